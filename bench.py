@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- DESC solve throughput on B200 (metric of BASELINE.json), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one complete DESC_init-equivalent solve (DESC.m:14-263 + GCW.m) of the workload:
+CSR incidence build + cycle inconsistencies + PGD (iterations actually run) + GCW recovery.
+Workload (configs[3] of BASELINE.json, the configuration the metric is quoted on; it fits one
+GPU): Uniform_Topology(n=10000, p=0.1, q=0.2, sigma=0.1, 'uniform'), params = {iters=100,
+Gradient=ConstantStepSize(0.01)} (Demo/compare_algorithms.m:39-45), reference sampling rule.
+
+value  = 3-cycle evaluations per second over the whole step = m_cycle * iters_run / step time,
+         inputs (Ind, RijMat) already resident in HBM; N>1 shards the same problem ("strong").
+e2e    = the same through the reference-style call with HOST (pinned) buffers: H2D of Ind/RijMat
+         and D2H of S_vec / R_est / history inside the timed region.
+roofline = the fused PGD-iteration kernel: algorithmic bytes (40*m_cycle + 12*m_pos + 8*m,
+         SURVEY 8d) / mean kernel duration (CUDA events on the launching stream) vs measured HBM peak.
+cpu_baseline = the oracle port timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "cfg4": dict(n=10000, p=0.1, q=0.2, sigma=0.1, model="uniform", iters=100, lr=0.01,
+                 name="Uniform_Topology n=10000 p=0.1 q=0.2 sigma=0.1 uniform, iters=100 ConstantStepSize(0.01)"),
+    "cfg2": dict(n=1000, p=0.5, q=0.3, sigma=0.1, model="uniform", iters=100, lr=0.01,
+                 name="Uniform_Topology n=1000 p=0.5 q=0.3 sigma=0.1 uniform, iters=100 ConstantStepSize(0.01)"),
+    "small": dict(n=2000, p=0.1, q=0.2, sigma=0.1, model="uniform", iters=100, lr=0.01,
+                  name="Uniform_Topology n=2000 p=0.1 q=0.2 sigma=0.1 uniform, iters=100 ConstantStepSize(0.01)"),
+}
+METRIC = "DESC 3-cycle evals/s (whole solve: incidence + d_ijk + PGD + GCW)"
+UNIT = "evals/s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port on a bounded sample of the workload
+# ------------------------------------------------------------------------------------------
+def cpu_sample(wl, n_sub, iters, seed=0):
+    """Oracle (numpy port of DESC.m / GCW.m) on the workload family at n_sub nodes with the same
+    edge density and sampling budget; returns evals/s over the whole solve, like `value`."""
+    import numpy as np
+    from oracle import desc_oracle as O
+    mo = O.uniform_topology(n_sub, wl["p"], wl["q"], wl["sigma"], wl["model"], rng=seed)
+    t0 = time.perf_counter()
+    inc = O.build_incidence(mo["Ind"], n_sample=None, seed=1)
+    S0 = O.cycle_inconsistency(inc, mo["RijMat"])
+    S_vec, hist, iters_run = O.pgd(inc, S0, iters, O.ConstantStepSize(wl["lr"]))
+    O.gcw(mo["Ind"], mo["RijMat"], S_vec)
+    dt = time.perf_counter() - t0
+    return inc.m_cycle * iters_run / dt, dt, dict(n=n_sub, m=int(inc.m), m_cycle=int(inc.m_cycle), iters=int(iters_run))
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sub, iters = args.cpu_n, args.cpu_iters
+    for _ in range(args.warmup and 1):
+        cpu_sample(wl, min(n_sub, 300), 2)
+    vals, times = [], []
+    info = None
+    for _ in range(max(args.steps, 1)):
+        v, dt, info = cpu_sample(wl, n_sub, iters)
+        vals.append(v)
+        times.append(dt)
+    value = statistics.mean(vals)
+    sample = ("oracle port (numpy, oracle/desc_oracle.py) of DESC.m:14-263 + GCW.m on the same graph family at "
+              "n=%d (m=%d, m_cycle=%d), %d PGD iterations per step" % (info["n"], info["m"], info["m_cycle"], info["iters"]))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(times),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["name"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_gpu(args, wl):
+    import numpy as np
+    import torch
+    import desc_b200
+    from desc_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    nccl_id = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=dev)
+
+    # ---- synthetic inputs, generated on rank 0's device and broadcast so every rank holds the same graph
+    if rank == 0:
+        mo = synth.uniform_topology(wl["n"], wl["p"], wl["q"], wl["sigma"], wl["model"], seed=args.seed, device=dev)
+        m_t = torch.tensor([mo["m"]], device=dev, dtype=torch.int64)
+    else:
+        mo = None
+        m_t = torch.zeros(1, device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.broadcast(m_t, 0)
+    m = int(m_t.item())
+    if rank == 0:
+        Ind_d, R_d = mo["Ind"].reshape(-1).contiguous(), mo["RijMat"].reshape(-1).contiguous()
+    else:
+        Ind_d = torch.empty(2 * m, device=dev, dtype=torch.float64)
+        R_d = torch.empty(9 * m, device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.broadcast(Ind_d, 0)
+        dist.broadcast(R_d, 0)
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(desc_b200.nccl_unique_id()), dtype=torch.uint8).to(dev)
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+    # pinned host copies for the end-to-end arm
+    Ind_h = torch.empty(2 * m, dtype=torch.float64).pin_memory()
+    R_h = torch.empty(9 * m, dtype=torch.float64).pin_memory()
+    Ind_h.copy_(Ind_d)
+    R_h.copy_(R_d)
+    Ind_np = Ind_h.numpy().reshape(2, m).T            # (m,2) Fortran view of the pinned buffer
+    R_np = R_h.numpy().reshape(m, 3, 3).transpose(2, 1, 0)   # (3,3,m) Fortran view of the pinned buffer
+    S_out = torch.empty(m, dtype=torch.float64).pin_memory()
+    R_out = torch.empty(9 * wl["n"], dtype=torch.float64).pin_memory()
+    stream = torch.cuda.current_stream(dev)
+    rule = desc_b200.ConstantStepSize(wl["lr"])
+    kw = dict(device=local, stream=stream.cuda_stream, rank=rank, world=world, nccl_id=nccl_id)
+    state = {}
+
+    def step_resident():
+        s = desc_b200.Solver(Ind_d, R_d, n=wl["n"], **kw)
+        try:
+            info = s.build_incidence(n_sample=0, seed=1)
+            s.cycle_inconsistency()
+            _, _, iters_run = s.pgd(wl["iters"], rule, want_S=False, want_hist=False)
+            s.gcw(want_R=False)
+            state.update(info=info, iters_run=iters_run, timings=s.timings())
+        finally:
+            s.close()
+
+    def step_e2e():
+        s = desc_b200.Solver(Ind_np, R_np, n=wl["n"], **kw)
+        try:
+            s.build_incidence(n_sample=0, seed=1)
+            s.cycle_inconsistency()
+            import ctypes as C
+            from desc_b200 import _lib
+            r = rule._to_c()
+            run = C.c_int32(0)
+            _lib.check(s._lib.desc_b200_pgd(s._h, wl["iters"], C.byref(r), C.c_void_p(S_out.data_ptr()), None, C.byref(run)))
+            _lib.check(s._lib.desc_b200_gcw(s._h, None, C.c_void_p(R_out.data_ptr())))
+            state.update(e2e_iters=int(run.value))
+        finally:
+            s.close()
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        launches = 0
+        for _ in range(steps):
+            fn()
+            launches += state.get("timings", {}).get("total_launches", 0)
+        ev1.record(stream)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), launches
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total, launches = timed(step_resident, args.steps)
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    info, iters_run, tm = state["info"], state["iters_run"], state["timings"]
+    evals = info["m_cycle"] * iters_run
+    value = evals / (ms_step * 1e-3)
+
+    step_e2e()
+    ms_e2e_total, _ = timed(step_e2e, max(1, min(args.steps, 3)))
+    ms_e2e = ms_e2e_total / max(1, min(args.steps, 3))
+    e2e = {"value": evals / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": (2 * m + 9 * m) * 8,
+           "d2h_bytes_per_step": (m + 9 * wl["n"]) * 8, "ms_per_step": ms_e2e}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        local_slots = info["local_slots"]
+        local_edges = info["edge_end"] - info["edge_begin"]
+        alg_bytes = 40.0 * local_slots + 12.0 * local_edges + 8.0 * info["m"]
+        iter_ms = tm["pgd_iter_ms"]
+        achieved = alg_bytes / (iter_ms * 1e-3) / 1e9 if iter_ms > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": "k_pgd_iter (fused PGD iteration)", "achieved": achieved, "peak": peak,
+                    "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": iter_ms,
+                    "formula": "40*slots + 12*edges_with_cycles + 8*m (SURVEY 8d), per rank"}
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            v, dt, ci = cpu_sample(wl, args.cpu_n, args.cpu_iters)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": "numpy oracle port on the same graph family at n=%d (m=%d, m_cycle=%d), %d PGD iterations, "
+                             "%.1f s" % (ci["n"], ci["m"], ci["m_cycle"], ci["iters"], dt)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": wl["name"], "n": wl["n"], "m": m, "m_pos": info["m_pos"],
+                           "m_cycle": info["m_cycle"], "n_sample": info["n_sample"], "iters_run": iters_run,
+                           "l2": "inputs_exceed_l2 (per-iteration working set %.1f GB)" % (alg_bytes / 1e9),
+                           "parallelism": "edge-sharded x%d" % world},
+                "solve_s": ms_step * 1e-3,
+                "pgd_evals_per_s": evals / (tm["pgd_ms"] * 1e-3) if tm["pgd_ms"] > 0 else None,
+                "stages_ms": {k: tm[k] for k in ("graph_ms", "build_ms", "cycle_ms", "pgd_ms", "gcw_ms", "pgd_iter_ms")},
+                "gcw_iters": tm["gcw_iters"], "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "cpu_baseline": cpu, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="desc_b200", choices=["desc_b200", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-n", type=int, default=1500, help="nodes of the CPU-baseline sample graph")
+    ap.add_argument("--cpu-iters", type=int, default=10, help="PGD iterations of the CPU-baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_gpu(args, wl)
+
+
+if __name__ == "__main__":
+    main()

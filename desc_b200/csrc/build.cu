@@ -1,0 +1,750 @@
+// Graph setup and CSR edge->3-cycle incidence build on device (reference: DESC.m:19-127).
+//
+// Data structures (all in HBM, built once):
+//   * adjacency bitmap  bm[n][nwords]  + per-word prefix popcounts bmprefix[n][nwords]
+//     -> "is k a common neighbour of i and j" is one AND, and the CSR position of (row, v) is
+//        bmprefix + popc, so the symmetric CSR (adj_nbr/adj_eid) is filled without any sort.
+//     replaces AdjMat (DESC.m:23-24), IndMat (DESC.m:67-68) and the dense DGEMM co-degree
+//     (DESC.m:29).
+//   * rowptr[m+1] (int64) / apex[m_cycle]: the CSR incidence = cum_ind / IJK (DESC.m:49,93),
+//     kept over ALL edges (edges without triangles have empty rows).
+//   * pk_jk / pk_ki: Ind_jk / Ind_ki (DESC.m:87-88) packed with the orientation bit and the
+//     IKJ_appears / JKI_appears flag (DESC.m:113,124).
+#include "internal.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+// error bits written by kernels into h->d_err[0]
+#define ERRB_RANGE 1
+#define ERRB_ORDER 2
+#define ERRB_NOTINT 4
+#define ERRB_APEX 8
+
+// ------------------------------------------------------------------------------------------
+// A1: Ind (m x 2 doubles, 1-based) -> ei/ej int32 0-based, with validation
+// ------------------------------------------------------------------------------------------
+__global__ void k_convert_ind(const double* __restrict__ Ind, int64_t m, int* __restrict__ ei,
+                              int* __restrict__ ej, int* __restrict__ err, int* __restrict__ nmax) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    double di = Ind[e], dj = Ind[m + e];
+    int bad = 0;
+    if (!(di >= 1.0) || !(dj > di) || !(dj <= 2147483647.0)) bad |= ERRB_RANGE;
+    if (di != floor(di) || dj != floor(dj)) bad |= ERRB_NOTINT;
+    if (!bad && e > 0) {
+        double pi = Ind[e - 1], pj = Ind[m + e - 1];
+        if (!(pi < di || (pi == di && pj < dj))) bad |= ERRB_ORDER;
+    }
+    if (bad) {
+        atomicOr(err, bad);
+        return;
+    }
+    ei[e] = (int)di - 1;
+    ej[e] = (int)dj - 1;
+    atomicMax(nmax, (int)dj);
+}
+
+__global__ void k_set_bits(const int* __restrict__ ei, const int* __restrict__ ej, int64_t m,
+                           uint32_t* __restrict__ bm, int nwords) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    int i = ei[e], j = ej[e];
+    atomicOr(&bm[(size_t)i * nwords + (j >> 5)], 1u << (j & 31));
+    atomicOr(&bm[(size_t)j * nwords + (i >> 5)], 1u << (i & 31));
+}
+
+// one warp per row: exclusive prefix of popcounts over the row's words, row degree
+__global__ void k_row_prefix(const uint32_t* __restrict__ bm, int* __restrict__ bmprefix,
+                             int* __restrict__ deg, int n, int nwords) {
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    int run = 0;
+    for (int base = 0; base < nwords; base += 32) {
+        int w = base + lane;
+        int c = (w < nwords) ? __popc(bm[(size_t)row * nwords + w]) : 0;
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (w < nwords) bmprefix[(size_t)row * nwords + w] = run + inc - c;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) deg[row] = run;
+}
+
+// single-block exclusive scan of n ints into n+1 ints (n is the node count: small)
+__global__ void k_scan_nodes(const int* __restrict__ deg, int* __restrict__ rowstart, int n,
+                             int* __restrict__ err_isolated) {
+    __shared__ int sh[1024];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        int idx = base + threadIdx.x;
+        int v = idx < n ? deg[idx] : 0;
+        if (idx < n && v == 0) atomicOr(err_isolated, 1);
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            int t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (idx < n) rowstart[idx] = carry + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) rowstart[n] = carry;
+}
+
+__global__ void k_fill_adj(const int* __restrict__ ei, const int* __restrict__ ej, int64_t m,
+                           const uint32_t* __restrict__ bm, const int* __restrict__ bmprefix,
+                           int nwords, const int* __restrict__ rowstart, int* __restrict__ adj_nbr,
+                           int* __restrict__ adj_eid) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    int i = ei[e], j = ej[e];
+    int pi = rowstart[i] + desc_rank(bm, bmprefix, nwords, i, j);
+    int pj = rowstart[j] + desc_rank(bm, bmprefix, nwords, j, i);
+    adj_nbr[pi] = j;
+    adj_eid[pi] = (int)e;
+    adj_nbr[pj] = i;
+    adj_eid[pj] = (int)e;
+}
+
+int desc_graph_setup(desc_b200_handle* h, const double* d_Ind) {
+    const int64_t m = h->m;
+    cudaStream_t st = h->stream;
+    CUDA_TRY(cudaMalloc(&h->d_err, 8 * sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(h->d_err, 0, 8 * sizeof(int), st));
+    CUDA_TRY(cudaMalloc(&h->ei, std::max<int64_t>(m, 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&h->ej, std::max<int64_t>(m, 1) * sizeof(int)));
+    const int TB = 256;
+    const unsigned gb = (unsigned)((m + TB - 1) / TB);
+    if (m > 0) {
+        k_convert_ind<<<gb, TB, 0, st>>>(d_Ind, m, h->ei, h->ej, h->d_err, h->d_err + 1);
+        KERNEL_CHECK(h);
+    }
+    int herr[2];
+    CUDA_TRY(cudaMemcpyAsync(herr, h->d_err, sizeof(herr), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (herr[0]) {
+        desc_set_error("Ind violates the layout contract (%s%s%s): rows must be 1-based integers "
+                       "with i<j, strictly sorted by (i,j) [DESC.m:31-37 matches edges to tril(:) "
+                       "order by position]",
+                       (herr[0] & ERRB_RANGE) ? "range " : "", (herr[0] & ERRB_ORDER) ? "order " : "",
+                       (herr[0] & ERRB_NOTINT) ? "non-integer" : "");
+        return DESC_B200_ERR_ARG;
+    }
+    int nmax = herr[1];
+    if (h->n <= 0) h->n = nmax;
+    if (nmax > h->n) {
+        desc_set_error("Ind references node %d but n=%d", nmax, h->n);
+        return DESC_B200_ERR_ARG;
+    }
+    if (h->n <= 0 || m <= 0) {
+        desc_set_error("empty graph (n=%d, m=%lld)", h->n, (long long)m);
+        return DESC_B200_ERR_ARG;
+    }
+    const int n = h->n;
+    h->nwords = (((n + 31) / 32) + 3) & ~3;  // rows are 16-byte aligned for uint4 loads
+    const size_t bmsz = (size_t)n * h->nwords;
+    if (bmsz * 8 > (size_t)24 << 30) {
+        desc_set_error("n=%d needs a %.1f GB adjacency bitmap; the sorted-list build path for very "
+                       "large sparse graphs is not implemented",
+                       n, bmsz * 8 / 1e9);
+        return DESC_B200_ERR_LIMIT;
+    }
+    CUDA_TRY(cudaMalloc(&h->bm, bmsz * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&h->bmprefix, bmsz * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&h->rowstart, (size_t)(n + 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&h->adj_nbr, 2 * m * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&h->adj_eid, 2 * m * sizeof(int)));
+    int* d_deg = nullptr;
+    CUDA_TRY(cudaMalloc(&d_deg, (size_t)n * sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(h->bm, 0, bmsz * sizeof(uint32_t), st));
+    k_set_bits<<<gb, TB, 0, st>>>(h->ei, h->ej, m, h->bm, h->nwords);
+    KERNEL_CHECK(h);
+    k_row_prefix<<<(n * 32 + TB - 1) / TB, TB, 0, st>>>(h->bm, h->bmprefix, d_deg, n, h->nwords);
+    KERNEL_CHECK(h);
+    k_scan_nodes<<<1, 1024, 0, st>>>(d_deg, h->rowstart, n, h->d_err + 2);
+    KERNEL_CHECK(h);
+    k_fill_adj<<<gb, TB, 0, st>>>(h->ei, h->ej, m, h->bm, h->bmprefix, h->nwords, h->rowstart,
+                                  h->adj_nbr, h->adj_eid);
+    KERNEL_CHECK(h);
+    int iso = 0;
+    CUDA_TRY(cudaMemcpyAsync(&iso, h->d_err + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaFree(d_deg));
+    if (iso) {
+        desc_set_error("a node in 1..n has no edge: GCW.m:21 would divide by zero (SURVEY H9)");
+        return DESC_B200_ERR_ARG;
+    }
+    return DESC_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// generic exclusive scan int32 -> int64 (three kernels)
+// ------------------------------------------------------------------------------------------
+#define SCAN_TB 256
+#define SCAN_PER 8
+#define SCAN_TILE (SCAN_TB * SCAN_PER)
+
+__global__ void k_scan_tile_sums(const int* __restrict__ in, int64_t count, int64_t* __restrict__ sums) {
+    __shared__ int64_t sh[SCAN_TB / 32];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    int64_t s = 0;
+    for (int x = 0; x < SCAN_PER; x++) {
+        int64_t idx = base + x * SCAN_TB + threadIdx.x;
+        if (idx < count) s += in[idx];
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t t = 0;
+        for (int x = 0; x < SCAN_TB / 32; x++) t += sh[x];
+        sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void k_scan_sums(int64_t* __restrict__ sums, int64_t nt) {
+    // single thread block, sequential over chunks; nt is small (count / 2048)
+    __shared__ int64_t sh[1024];
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < nt; base += 1024) {
+        int64_t idx = base + threadIdx.x;
+        int64_t v = idx < nt ? sums[idx] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            int64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (idx < nt) sums[idx] = carry + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += sh[1023];
+        __syncthreads();
+    }
+}
+
+__global__ void k_scan_apply(const int* __restrict__ in, int64_t count,
+                             const int64_t* __restrict__ sums, int64_t* __restrict__ out) {
+    // thread t owns SCAN_PER consecutive elements of the tile
+    __shared__ int64_t sh[SCAN_TB];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_PER;
+    int v[SCAN_PER];
+    int64_t s = 0;
+#pragma unroll
+    for (int x = 0; x < SCAN_PER; x++) {
+        v[x] = (base + x < count) ? in[base + x] : 0;
+        s += v[x];
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < SCAN_TB; o <<= 1) {
+        int64_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    int64_t run = sums[blockIdx.x] + sh[threadIdx.x] - s;
+#pragma unroll
+    for (int x = 0; x < SCAN_PER; x++) {
+        if (base + x < count) out[base + x] = run;
+        run += v[x];
+    }
+    if (base <= count - 1 && base + SCAN_PER > count - 1) out[count] = run;  // total
+}
+
+int desc_exclusive_scan_i64(desc_b200_handle* h, const int* in, int64_t* out, int64_t count) {
+    // out has count+1 entries; out[count] = total
+    if (count == 0) {
+        CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(int64_t), h->stream));
+        return DESC_B200_OK;
+    }
+    int64_t nt = (count + SCAN_TILE - 1) / SCAN_TILE;
+    int64_t* sums = nullptr;
+    CUDA_TRY(cudaMalloc(&sums, nt * sizeof(int64_t)));
+    k_scan_tile_sums<<<(unsigned)nt, SCAN_TB, 0, h->stream>>>(in, count, sums);
+    KERNEL_CHECK(h);
+    k_scan_sums<<<1, 1024, 0, h->stream>>>(sums, nt);
+    KERNEL_CHECK(h);
+    k_scan_apply<<<(unsigned)nt, SCAN_TB, 0, h->stream>>>(in, count, sums, out);
+    KERNEL_CHECK(h);
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaFree(sums));
+    return DESC_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// A2: co-degree of every edge = popc(bm[i] & bm[j])  (replaces (A*A).*A, DESC.m:29)
+// one warp per edge, 128-bit loads; consecutive edges share row i, so it stays in L1
+// ------------------------------------------------------------------------------------------
+__global__ void k_codeg(const int* __restrict__ ei, const int* __restrict__ ej, int64_t e0,
+                        int64_t e1, const uint32_t* __restrict__ bm, int nwords,
+                        int* __restrict__ codeg) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nq = nwords >> 2;
+    for (int64_t e = e0 + warp; e < e1; e += nwarps) {
+        const uint4* ri = reinterpret_cast<const uint4*>(bm + (size_t)ei[e] * nwords);
+        const uint4* rj = reinterpret_cast<const uint4*>(bm + (size_t)ej[e] * nwords);
+        int c = 0;
+        for (int q = lane; q < nq; q += 32) {
+            uint4 a = ri[q], b = rj[q];
+            c += __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
+        }
+        c = group_sum_int<32>(c);
+        if (lane == 0) codeg[e] = c;
+    }
+}
+
+__global__ void k_hist(const int* __restrict__ codeg, int64_t m, int* __restrict__ hist) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    int c = codeg[e];
+    // warp-aggregate equal values (co-degrees cluster tightly around n*p^2)
+    unsigned peers = __match_any_sync(__activemask(), c);
+    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[c], __popc(peers));
+}
+
+__global__ void k_ns(const int* __restrict__ codeg, int64_t m, int n_sample, int* __restrict__ ns) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e < m) ns[e] = min(codeg[e], n_sample);
+}
+
+__global__ void k_ns_from_ptr(const int64_t* __restrict__ ptr, int64_t m, int* __restrict__ ns) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e < m) ns[e] = (int)(ptr[e + 1] - ptr[e]);
+}
+
+// ------------------------------------------------------------------------------------------
+// A3: fill the incidence.  One warp per edge: enumerate common neighbours in ascending order
+// from the AND of the two bitmap rows; if the co-degree exceeds the budget keep the n_sample
+// smallest sampler keys (rank counting in shared memory); emit apex + packed partner edges.
+// ------------------------------------------------------------------------------------------
+struct FillArgs {
+    const int *ei, *ej;
+    const uint32_t* bm;
+    const int* bmprefix;
+    int nwords;
+    const int *rowstart, *adj_eid;
+    const int* codeg;
+    const int64_t* rowptr;
+    int* apex;              // global slot index
+    uint32_t *pk_jk, *pk_ki;  // local slot index (slot - slot_base), may be null (apex only)
+    int64_t e0, e1;         // edges to process
+    int64_t l0, l1;         // local edge range for pk_* output
+    int64_t slot_base;
+    int n_sample, maxc;
+    uint64_t seed;
+};
+
+__global__ void k_fill_slots(FillArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    // per-warp scratch: keys (8B) | k (4B) | sel (1B)
+    const size_t per_warp = ((size_t)a.maxc * 13 + 15) & ~(size_t)15;
+    unsigned char* base = smem_raw + per_warp * wib;
+    uint64_t* ckey = reinterpret_cast<uint64_t*>(base);
+    int* ck = reinterpret_cast<int*>(base + (size_t)a.maxc * 8);
+    unsigned char* csel = base + (size_t)a.maxc * 12;
+
+    const int64_t warp = (int64_t)blockIdx.x * wpb + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * wpb;
+    for (int64_t e = a.e0 + warp; e < a.e1; e += nwarps) {
+        const int c = a.codeg[e];
+        if (c == 0) continue;
+        const int i = a.ei[e], j = a.ej[e];
+        const uint32_t* ri = a.bm + (size_t)i * a.nwords;
+        const uint32_t* rj = a.bm + (size_t)j * a.nwords;
+        // enumerate candidates in ascending k
+        int run = 0;
+        for (int wb = 0; wb < a.nwords; wb += 32) {
+            int w = wb + lane;
+            uint32_t x = (w < a.nwords) ? (ri[w] & rj[w]) : 0u;
+            int cnt = __popc(x);
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            int pos = run + inc - cnt;
+            while (x) {
+                int b = __ffs(x) - 1;
+                x &= x - 1;
+                ck[pos++] = (w << 5) + b;
+            }
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        __syncwarp();
+        const bool sample = c > a.n_sample;  // len==n_sample keeps everything (DESC.m:83)
+        if (sample) {
+            for (int q = lane; q < c; q += 32) ckey[q] = desc_key(a.seed, (uint64_t)e, (uint64_t)ck[q]);
+            __syncwarp();
+            for (int q = lane; q < c; q += 32) {
+                const uint64_t kq = ckey[q];
+                const int vq = ck[q];
+                int rank = 0;
+                for (int r = 0; r < c; r++) {
+                    uint64_t kr = ckey[r];
+                    rank += (kr < kq) || (kr == kq && ck[r] < vq);
+                }
+                csel[q] = rank < a.n_sample;
+            }
+            __syncwarp();
+        }
+        // compaction + output
+        const int64_t r0 = a.rowptr[e];
+        const bool local = (e >= a.l0 && e < a.l1) && a.pk_jk != nullptr;
+        int outpos = 0;
+        for (int qb = 0; qb < c; qb += 32) {
+            int q = qb + lane;
+            bool sel = q < c && (!sample || csel[q]);
+            unsigned bal = __ballot_sync(0xffffffffu, sel);
+            if (sel) {
+                int p = outpos + __popc(bal & ((1u << lane) - 1u));
+                int k = ck[q];
+                a.apex[r0 + p] = k;
+                if (local) {
+                    int eik = a.adj_eid[a.rowstart[i] + desc_rank(a.bm, a.bmprefix, a.nwords, i, k)];
+                    int ejk = a.adj_eid[a.rowstart[j] + desc_rank(a.bm, a.bmprefix, a.nwords, j, k)];
+                    a.pk_ki[r0 - a.slot_base + p] = (uint32_t)eik | (i < k ? PK_SEL : 0u);
+                    a.pk_jk[r0 - a.slot_base + p] = (uint32_t)ejk | (j < k ? PK_SEL : 0u);
+                }
+            }
+            outpos += __popc(bal);
+        }
+        __syncwarp();
+    }
+}
+
+// explicit cycle lists: apex is given; compute packed partner edges and validate
+__global__ void k_fill_explicit(FillArgs a, int* __restrict__ err) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = a.l0 + warp; e < a.l1; e += nwarps) {
+        const int i = a.ei[e], j = a.ej[e];
+        const int64_t r0 = a.rowptr[e], r1 = a.rowptr[e + 1];
+        for (int64_t s = r0 + lane; s < r1; s += 32) {
+            int k = a.apex[s];
+            bool ok = k >= 0 && (k >> 5) < a.nwords;
+            if (ok) {
+                uint32_t bit = 1u << (k & 31);
+                ok = (a.bm[(size_t)i * a.nwords + (k >> 5)] & bit) &&
+                     (a.bm[(size_t)j * a.nwords + (k >> 5)] & bit);
+            }
+            if (!ok) {
+                atomicOr(err, ERRB_APEX);
+                continue;
+            }
+            int eik = a.adj_eid[a.rowstart[i] + desc_rank(a.bm, a.bmprefix, a.nwords, i, k)];
+            int ejk = a.adj_eid[a.rowstart[j] + desc_rank(a.bm, a.bmprefix, a.nwords, j, k)];
+            a.pk_ki[s - a.slot_base] = (uint32_t)eik | (i < k ? PK_SEL : 0u);
+            a.pk_jk[s - a.slot_base] = (uint32_t)ejk | (j < k ? PK_SEL : 0u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// A4: reciprocal-slot flags.  Slot (ij;k): IKJ_appears <=> j is in the apex list of edge {i,k};
+// JKI_appears <=> i is in the apex list of edge {j,k}  (DESC.m:111-125).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool apex_bsearch(const int* __restrict__ apex, int64_t lo, int64_t hi,
+                                             int v) {
+    const int64_t end = hi;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (apex[mid] < v)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo < end && apex[lo] == v;
+}
+
+__device__ __forceinline__ bool apex_lsearch(const int* __restrict__ apex, int64_t lo, int64_t hi,
+                                             int v) {
+    for (int64_t s = lo; s < hi; s++)
+        if (apex[s] == v) return true;
+    return false;
+}
+
+template <bool SORTED>
+__global__ void k_recip_flags(const int* __restrict__ ei, const int* __restrict__ ej,
+                              const int64_t* __restrict__ rowptr, const int* __restrict__ apex,
+                              uint32_t* __restrict__ pk_jk, uint32_t* __restrict__ pk_ki, int64_t l0,
+                              int64_t l1, int64_t slot_base) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = l0 + warp; e < l1; e += nwarps) {
+        const int i = ei[e], j = ej[e];
+        const int64_t r0 = rowptr[e], r1 = rowptr[e + 1];
+        for (int64_t s = r0 + lane; s < r1; s += 32) {
+            uint32_t pki = pk_ki[s - slot_base], pjk = pk_jk[s - slot_base];
+            int64_t eik = pki & PK_MASK, ejk = pjk & PK_MASK;
+            bool fa = SORTED ? apex_bsearch(apex, rowptr[eik], rowptr[eik + 1], j)
+                             : apex_lsearch(apex, rowptr[eik], rowptr[eik + 1], j);
+            bool fb = SORTED ? apex_bsearch(apex, rowptr[ejk], rowptr[ejk + 1], i)
+                             : apex_lsearch(apex, rowptr[ejk], rowptr[ejk + 1], i);
+            pk_ki[s - slot_base] = (pki & ~PK_APP) | (fa ? PK_APP : 0u);
+            pk_jk[s - slot_base] = (pjk & ~PK_APP) | (fb ? PK_APP : 0u);
+        }
+    }
+}
+
+// slot-balanced contiguous edge ranges: boundary r = first edge whose rowptr >= r*m_cycle/world
+__global__ void k_shard_bounds(const int64_t* __restrict__ rowptr, int64_t m, int64_t m_cycle,
+                               int world, int64_t* __restrict__ bounds) {
+    int r = threadIdx.x;
+    if (r > world) return;
+    if (r == 0) {
+        bounds[0] = 0;
+        return;
+    }
+    if (r == world) {
+        bounds[world] = m;
+        return;
+    }
+    int64_t target = (m_cycle * r) / world;
+    int64_t lo = 0, hi = m;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (rowptr[mid] < target)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    bounds[r] = lo;
+}
+
+static void free_incidence(desc_b200_handle* h) {
+    cudaFree(h->rowptr);
+    cudaFree(h->apex);
+    cudaFree(h->pk_jk);
+    cudaFree(h->pk_ki);
+    cudaFree(h->S0);
+    for (int b = 0; b < 2; b++) {
+        cudaFree(h->w[b]);
+        h->w[b] = nullptr;
+    }
+    cudaFree(h->adam_m);
+    cudaFree(h->adam_v);
+    h->rowptr = nullptr;
+    h->apex = nullptr;
+    h->pk_jk = h->pk_ki = nullptr;
+    h->S0 = nullptr;
+    h->adam_m = h->adam_v = nullptr;
+    h->built = h->have_s0 = h->have_pgd = false;
+}
+
+int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t seed,
+                              const int64_t* cyc_ptr, const int32_t* cyc_apex) {
+    const int64_t m = h->m;
+    const int n = h->n;
+    cudaStream_t st = h->stream;
+    const int TB = 256;
+    const unsigned gb = (unsigned)((m + TB - 1) / TB);
+    free_incidence(h);
+    if (!h->codeg) CUDA_TRY(cudaMalloc(&h->codeg, m * sizeof(int)));
+    const int warp_grid = DESC_SMS * 8;  // 8 CTAs of 8 warps per SM, grid-stride over edges
+
+    // ---- co-degrees of all edges.  Multi-GPU: every rank counts an equal slice, then all-gather.
+    {
+        std::vector<int64_t> b(h->world + 1);
+        for (int r = 0; r <= h->world; r++) b[r] = (m * r) / h->world;
+        k_codeg<<<warp_grid, 256, 0, st>>>(h->ei, h->ej, b[h->rank], b[h->rank + 1], h->bm, h->nwords,
+                                           h->codeg);
+        KERNEL_CHECK(h);
+        DESC_TRY(desc_allgather_ranges(h, h->codeg, sizeof(int), b));
+    }
+    // ---- histogram -> m_pos, max co-degree, sampling budget (DESC.m:36-43)
+    int* d_hist = nullptr;
+    CUDA_TRY(cudaMalloc(&d_hist, (size_t)(n + 1) * sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(d_hist, 0, (size_t)(n + 1) * sizeof(int), st));
+    k_hist<<<gb, TB, 0, st>>>(h->codeg, m, d_hist);
+    KERNEL_CHECK(h);
+    std::vector<int> hist(n + 1);
+    CUDA_TRY(cudaMemcpyAsync(hist.data(), d_hist, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaFree(d_hist));
+    int64_t m_pos = 0;
+    int maxc = 0;
+    for (int c = 1; c <= n; c++)
+        if (hist[c]) {
+            m_pos += hist[c];
+            maxc = c;
+        }
+    h->m_pos = m_pos;
+    h->max_codeg = maxc;
+
+    int* d_ns = nullptr;
+    CUDA_TRY(cudaMalloc(&d_ns, m * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&h->rowptr, (m + 1) * sizeof(int64_t)));
+    const bool explicit_lists = cyc_ptr != nullptr;
+    if (explicit_lists) {
+        if (!cyc_apex) {
+            desc_set_error("cyc_ptr given without cyc_apex");
+            return DESC_B200_ERR_ARG;
+        }
+        if (cyc_ptr[0] != 0) {
+            desc_set_error("cyc_ptr[0] must be 0");
+            return DESC_B200_ERR_ARG;
+        }
+        int mx = 0;
+        for (int64_t e = 0; e < m; e++) {
+            int64_t d = cyc_ptr[e + 1] - cyc_ptr[e];
+            if (d < 0 || d > n) {
+                desc_set_error("cyc_ptr is not a valid row pointer at edge %lld", (long long)e);
+                return DESC_B200_ERR_ARG;
+            }
+            mx = std::max<int>(mx, (int)d);
+        }
+        h->n_sample = mx;
+        h->m_cycle = cyc_ptr[m];
+        CUDA_TRY(cudaMemcpyAsync(h->rowptr, cyc_ptr, (m + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        k_ns_from_ptr<<<gb, TB, 0, st>>>(h->rowptr, m, d_ns);
+        KERNEL_CHECK(h);
+        h->apex_sorted = false;
+    } else {
+        int ns;
+        if (n_sample_req > 0)
+            ns = n_sample_req;
+        else if (n_sample_req < 0)
+            ns = std::max(maxc, 1);
+        else {
+            // MATLAB median of the positive co-degrees from the histogram (DESC.m:43)
+            double med = 0.0;
+            if (m_pos > 0) {
+                int64_t lo_idx = (m_pos - 1) / 2, hi_idx = m_pos / 2;  // 0-based order statistics
+                int64_t cum = 0;
+                int vlo = -1, vhi = -1;
+                for (int c = 1; c <= n && vhi < 0; c++) {
+                    cum += hist[c];
+                    if (vlo < 0 && cum > lo_idx) vlo = c;
+                    if (vhi < 0 && cum > hi_idx) vhi = c;
+                }
+                med = 0.5 * ((double)vlo + (double)vhi);
+            }
+            ns = std::max((int)std::ceil(med / 4.0), 30);
+        }
+        h->n_sample = ns;
+        k_ns<<<gb, TB, 0, st>>>(h->codeg, m, ns, d_ns);
+        KERNEL_CHECK(h);
+        DESC_TRY(desc_exclusive_scan_i64(h, d_ns, h->rowptr, m));
+        CUDA_TRY(cudaMemcpyAsync(&h->m_cycle, h->rowptr + m, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        h->apex_sorted = true;
+    }
+    h->max_ns = std::min(h->n_sample, std::max(maxc, 1));
+    if (explicit_lists) h->max_ns = h->n_sample;
+    CUDA_TRY(cudaFree(d_ns));
+
+    // ---- shard: slot-balanced contiguous edge ranges
+    h->shard_edges.assign(h->world + 1, 0);
+    {
+        int64_t* d_b = nullptr;
+        CUDA_TRY(cudaMalloc(&d_b, (h->world + 1) * sizeof(int64_t)));
+        k_shard_bounds<<<1, 64, 0, st>>>(h->rowptr, m, h->m_cycle, h->world, d_b);
+        KERNEL_CHECK(h);
+        CUDA_TRY(cudaMemcpyAsync(h->shard_edges.data(), d_b, (h->world + 1) * sizeof(int64_t),
+                                 cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaFree(d_b));
+    }
+    h->e_begin = h->shard_edges[h->rank];
+    h->e_end = h->shard_edges[h->rank + 1];
+    h->shard_slots.assign(h->world + 1, 0);
+    for (int r = 0; r <= h->world; r++)
+        CUDA_TRY(cudaMemcpyAsync(&h->shard_slots[r], h->rowptr + h->shard_edges[r], sizeof(int64_t),
+                                 cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    h->slot_base = h->shard_slots[h->rank];
+    h->n_slots = h->shard_slots[h->rank + 1] - h->slot_base;
+
+    const size_t ns_alloc = (size_t)std::max<int64_t>(h->n_slots, 1);
+    CUDA_TRY(cudaMalloc(&h->apex, (size_t)std::max<int64_t>(h->m_cycle, 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&h->pk_jk, ns_alloc * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&h->pk_ki, ns_alloc * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&h->S0, ns_alloc * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->w[0], ns_alloc * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->w[1], ns_alloc * sizeof(double)));
+
+    FillArgs fa;
+    fa.ei = h->ei;
+    fa.ej = h->ej;
+    fa.bm = h->bm;
+    fa.bmprefix = h->bmprefix;
+    fa.nwords = h->nwords;
+    fa.rowstart = h->rowstart;
+    fa.adj_eid = h->adj_eid;
+    fa.codeg = h->codeg;
+    fa.rowptr = h->rowptr;
+    fa.apex = h->apex;
+    fa.pk_jk = h->pk_jk;
+    fa.pk_ki = h->pk_ki;
+    fa.e0 = h->e_begin;
+    fa.e1 = h->e_end;
+    fa.l0 = h->e_begin;
+    fa.l1 = h->e_end;
+    fa.slot_base = h->slot_base;
+    fa.n_sample = h->n_sample;
+    fa.maxc = std::max(maxc, 1);
+    fa.seed = seed;
+    if (h->m_cycle > 0) {
+        if (explicit_lists) {
+            CUDA_TRY(cudaMemcpyAsync(h->apex, cyc_apex, h->m_cycle * sizeof(int), cudaMemcpyHostToDevice, st));
+            k_fill_explicit<<<warp_grid, 256, 0, st>>>(fa, h->d_err);
+            KERNEL_CHECK(h);
+            int herr = 0;
+            CUDA_TRY(cudaMemcpyAsync(&herr, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            if (herr & ERRB_APEX) {
+                CUDA_TRY(cudaMemsetAsync(h->d_err, 0, sizeof(int), st));
+                desc_set_error("explicit cycle list contains an apex that is not a common neighbour");
+                return DESC_B200_ERR_ARG;
+            }
+        } else {
+            const size_t per_warp = ((size_t)fa.maxc * 13 + 15) & ~(size_t)15;
+            int wpb = 8;
+            while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
+            if (per_warp * wpb > 220 * 1024) {
+                desc_set_error("max co-degree %d exceeds the shared-memory sampler scratch", maxc);
+                return DESC_B200_ERR_LIMIT;
+            }
+            const size_t smem = per_warp * wpb;
+            CUDA_TRY(cudaFuncSetAttribute(k_fill_slots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
+            k_fill_slots<<<DESC_SMS * ctas_per_sm, wpb * 32, smem, st>>>(fa);
+            KERNEL_CHECK(h);
+            // reciprocal flags need every edge's apex list
+            DESC_TRY(desc_allgather_ranges(h, h->apex, sizeof(int), h->shard_slots));
+        }
+        if (h->apex_sorted)
+            k_recip_flags<true><<<warp_grid, 256, 0, st>>>(h->ei, h->ej, h->rowptr, h->apex, h->pk_jk,
+                                                          h->pk_ki, h->e_begin, h->e_end, h->slot_base);
+        else
+            k_recip_flags<false><<<warp_grid, 256, 0, st>>>(h->ei, h->ej, h->rowptr, h->apex, h->pk_jk,
+                                                           h->pk_ki, h->e_begin, h->e_end, h->slot_base);
+        KERNEL_CHECK(h);
+    }
+    h->built = true;
+    return DESC_B200_OK;
+}

@@ -1,0 +1,130 @@
+// Multi-GPU plumbing: one process per GPU, NCCL over NVLink/NVSwitch.
+//
+// The reference has no communication layer at all (single MATLAB process); what is exchanged
+// here follows from sharding DESC.m's per-edge loops over contiguous edge ranges:
+//   * per PGD iteration: all-reduce (sum) of the 2m partner-sum accumulators + 2 scalars
+//     (DESC.m:189-190 in scatter form, DESC.m:232-233) and all-gather of the S_vec shards
+//     (DESC.m:193 gathers S at arbitrary edges);
+//   * per GCW power step: all-gather of the per-node 3x3 blocks (9n doubles);
+//   * once in the build: all-gather of co-degrees and apex lists.
+//
+// NCCL is bound at run time with dlopen, so the single-GPU library (and the MEX file that wraps
+// it) has no link-time dependency on NCCL; inside a torch process the already-loaded
+// torch-bundled libnccl.so.2 is reused.
+#include "internal.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+
+int nccl_load() {
+    if (g_nccl.ok) return DESC_B200_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) {
+        desc_set_error("multi-GPU requested but libnccl.so.2 cannot be loaded: %s", dlerror());
+        return DESC_B200_ERR_NCCL;
+    }
+#define LOAD(field, sym)                                                              \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, sym);                                \
+    if (!g_nccl.field) {                                                              \
+        desc_set_error("libnccl is missing symbol %s", sym);                          \
+        return DESC_B200_ERR_NCCL;                                                    \
+    }
+    LOAD(GetUniqueId, "ncclGetUniqueId");
+    LOAD(CommInitRank, "ncclCommInitRank");
+    LOAD(CommDestroy, "ncclCommDestroy");
+    LOAD(AllReduce, "ncclAllReduce");
+    LOAD(Broadcast, "ncclBroadcast");
+    LOAD(AllGather, "ncclAllGather");
+    LOAD(GroupStart, "ncclGroupStart");
+    LOAD(GroupEnd, "ncclGroupEnd");
+    LOAD(GetErrorString, "ncclGetErrorString");
+#undef LOAD
+    g_nccl.ok = true;
+    return DESC_B200_OK;
+}
+}  // namespace
+
+#define NCCL_TRY(expr)                                                                        \
+    do {                                                                                      \
+        ncclResult_t _r = (expr);                                                             \
+        if (_r != ncclSuccess) {                                                              \
+            desc_set_error("NCCL error at %s:%d: %s", __FILE__, __LINE__, g_nccl.GetErrorString(_r)); \
+            return DESC_B200_ERR_NCCL;                                                        \
+        }                                                                                     \
+    } while (0)
+
+extern "C" int desc_b200_nccl_unique_id(void* out128) {
+    if (!out128) {
+        desc_set_error("null output");
+        return DESC_B200_ERR_ARG;
+    }
+    DESC_TRY(nccl_load());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+    return DESC_B200_OK;
+}
+
+int desc_comm_init(desc_b200_handle* h, const void* nccl_id) {
+    if (h->world <= 1) return DESC_B200_OK;
+    if (!nccl_id) {
+        desc_set_error("world=%d but no nccl_id in opts", h->world);
+        return DESC_B200_ERR_ARG;
+    }
+    DESC_TRY(nccl_load());
+    ncclUniqueId id;
+    memcpy(&id, nccl_id, sizeof(id));
+    ncclComm_t comm;
+    NCCL_TRY(g_nccl.CommInitRank(&comm, h->world, id, h->rank));
+    h->comm = comm;
+    return DESC_B200_OK;
+}
+
+void desc_comm_destroy(desc_b200_handle* h) {
+    if (h->comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)h->comm);
+    h->comm = nullptr;
+}
+
+int desc_allreduce_sum(desc_b200_handle* h, double* buf, int64_t count) {
+    if (h->world <= 1 || count <= 0) return DESC_B200_OK;
+    NCCL_TRY(g_nccl.AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclSum, (ncclComm_t)h->comm, h->stream));
+    h->collectives++;
+    return DESC_B200_OK;
+}
+
+// in-place ragged all-gather: rank r owns elements [bounds[r], bounds[r+1]) of buf
+int desc_allgather_ranges(desc_b200_handle* h, void* buf, size_t elem_bytes,
+                          const std::vector<int64_t>& bounds) {
+    if (h->world <= 1) return DESC_B200_OK;
+    NCCL_TRY(g_nccl.GroupStart());
+    for (int r = 0; r < h->world; r++) {
+        const int64_t cnt = bounds[r + 1] - bounds[r];
+        if (cnt <= 0) continue;
+        char* p = (char*)buf + (size_t)bounds[r] * elem_bytes;
+        NCCL_TRY(g_nccl.Broadcast(p, p, (size_t)cnt * elem_bytes, ncclInt8, r, (ncclComm_t)h->comm, h->stream));
+    }
+    NCCL_TRY(g_nccl.GroupEnd());
+    h->collectives++;
+    return DESC_B200_OK;
+}

@@ -1,0 +1,172 @@
+// Internal declarations shared by the translation units of libdesc_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/desc_b200.h"
+
+#include <string.h>
+
+// ---- error plumbing -----------------------------------------------------------------
+void desc_set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            desc_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__,      \
+                           __LINE__, cudaGetErrorString(_e));                                 \
+            return DESC_B200_ERR_CUDA;                                                        \
+        }                                                                                     \
+    } while (0)
+
+#define DESC_TRY(expr)                                                                        \
+    do {                                                                                      \
+        int _r = (expr);                                                                      \
+        if (_r != DESC_B200_OK) return _r;                                                    \
+    } while (0)
+
+#define KERNEL_CHECK(h)                                                                       \
+    do {                                                                                      \
+        (h)->launches++;                                                                      \
+        CUDA_TRY(cudaGetLastError());                                                         \
+    } while (0)
+
+// ---- packed partner-edge words ------------------------------------------------------
+// pk_ki = e_ki | (i<k ? SEL : 0) | (IKJ_appears ? APP : 0)
+// pk_jk = e_jk | (j<k ? SEL : 0) | (JKI_appears ? APP : 0)
+// SEL says the vertex shared with the partner edge is that edge's smaller endpoint; it selects
+// the partner-sum accumulator (0 = via min endpoint, 1 = via max endpoint) and, for d_ijk, the
+// orientation of the stored relative rotation.
+#define PK_APP 0x80000000u
+#define PK_SEL 0x40000000u
+#define PK_MASK 0x3FFFFFFFu
+#define DESC_MAX_EDGES 0x3FFFFFFFll
+
+static constexpr int DESC_SMS = 148;  // B200
+static constexpr int DESC_GCW_MAXIT = 4000;
+
+struct desc_b200_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int rank = 0, world = 1;
+    void* comm = nullptr;       // ncclComm_t (comm.cu)
+    int launches = 0;
+    int collectives = 0;
+
+    // graph ---------------------------------------------------------------------------
+    int n = 0;
+    int64_t m = 0;
+    int* ei = nullptr;          // m, 0-based smaller endpoint
+    int* ej = nullptr;          // m
+    const double* Rij = nullptr;  // 9m, MATLAB layout
+    double* Rij_owned = nullptr;
+    int nwords = 0;             // 32-bit words per adjacency bitmap row
+    uint32_t* bm = nullptr;     // n x nwords adjacency bitmap
+    int* bmprefix = nullptr;    // n x nwords: set bits before each word of the row
+    int* rowstart = nullptr;    // n+1: CSR offsets of the symmetric adjacency
+    int* adj_nbr = nullptr;     // 2m: neighbours, ascending within a row
+    int* adj_eid = nullptr;     // 2m: edge id of (row, neighbour)
+
+    // incidence -----------------------------------------------------------------------
+    bool built = false, have_s0 = false, have_pgd = false;
+    bool apex_sorted = true;
+    int* codeg = nullptr;       // m
+    int n_sample = 0, max_codeg = 0, max_ns = 0;
+    int64_t m_pos = 0, m_cycle = 0;
+    int64_t* rowptr = nullptr;  // m+1 over ALL edges (empty rows for edges without triangles)
+    int* apex = nullptr;        // m_cycle (global): k of every slot
+    int64_t e_begin = 0, e_end = 0;   // local edge range (sharding); [0,m) when world==1
+    int64_t slot_base = 0, n_slots = 0;  // local slots = [slot_base, slot_base+n_slots)
+    std::vector<int64_t> shard_edges;  // world+1 edge boundaries
+    std::vector<int64_t> shard_slots;  // world+1 slot boundaries (rowptr at shard_edges)
+    uint32_t* pk_jk = nullptr;  // n_slots
+    uint32_t* pk_ki = nullptr;  // n_slots
+    double* S0 = nullptr;       // n_slots
+
+    // PGD state -------------------------------------------------------------------------
+    double* w[2] = {nullptr, nullptr};     // n_slots each (ping-pong)
+    double* S[2] = {nullptr, nullptr};     // m each
+    double* acc[2] = {nullptr, nullptr};   // 2m+2 each: partner sums via min/max endpoint, + [obj, change]
+    double* adam_m = nullptr;
+    double* adam_v = nullptr;
+    int final_buf = 0;                      // which ping-pong buffer holds the result
+    double* d_hist = nullptr;               // 2*iters
+    int hist_cap = 0;
+    int* d_ctrl = nullptr;                  // [0]=stopped [1]=final_iter [2]=misses
+    double* d_ctrl_f = nullptr;             // [0]=previous objective
+    int* h_ctrl = nullptr;                  // pinned mirror of d_ctrl
+
+    // GCW -------------------------------------------------------------------------------
+    double* omega = nullptr;    // m
+    double* isd = nullptr;      // n: 1/sqrt(d_i)
+    double* X[2] = {nullptr, nullptr};  // 9n each
+    double* gcw_coef = nullptr; // m: omega_e / sqrt(d_i d_j)
+    double* gcw_red = nullptr;  // reduction scratch
+    double* gcw_small = nullptr;  // 3x3 transforms etc.
+    double* gcw_res = nullptr;  // residual history (device)
+    double* gcw_res_host = nullptr;  // pinned mirror
+    double gcw_last_res = 0.0;
+    double gcw_theta[3] = {0.0, 0.0, 0.0};  // Ritz values of the last gcw call
+    double* R_est = nullptr;    // 9n
+    double* d_Sin = nullptr;    // m: S_vec passed to gcw from the host
+    bool have_gcw = false;
+
+    // scratch ---------------------------------------------------------------------------
+    int* d_err = nullptr;       // device error flags
+    desc_b200_timings tm = {};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+};
+
+// ---- stage implementations (one .cu each) ---------------------------------------------
+int desc_graph_setup(desc_b200_handle* h, const double* d_Ind);
+int desc_build_incidence_impl(desc_b200_handle* h, int n_sample, uint64_t seed,
+                              const int64_t* cyc_ptr, const int32_t* cyc_apex);
+int desc_cycle_impl(desc_b200_handle* h);
+int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int* iters_run);
+int desc_gcw_impl(desc_b200_handle* h, const double* d_S);
+int desc_exclusive_scan_i64(desc_b200_handle* h, const int* in, int64_t* out, int64_t count);
+
+// multi-GPU collectives (comm.cu); no-ops when world==1
+int desc_comm_init(desc_b200_handle* h, const void* nccl_id);
+void desc_comm_destroy(desc_b200_handle* h);
+int desc_allreduce_sum(desc_b200_handle* h, double* buf, int64_t count);
+int desc_allgather_ranges(desc_b200_handle* h, void* buf, size_t elem_bytes,
+                          const std::vector<int64_t>& bounds);
+
+// ---- device helpers -----------------------------------------------------------------
+#ifdef __CUDACC__
+// 64-bit sampler key of (edge, apex); bit-identical to oracle/desc_oracle.py::sampler_keys
+__host__ __device__ __forceinline__ uint64_t desc_key(uint64_t seed, uint64_t edge, uint64_t k) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (edge + 1ull);
+    z ^= 0xD1B54A32D192ED03ull * (k + 1ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// number of neighbours of `row` that are < v, and whether v is a neighbour
+__device__ __forceinline__ int desc_rank(const uint32_t* __restrict__ bm,
+                                         const int* __restrict__ bmprefix, int nwords, int row,
+                                         int v) {
+    const size_t o = (size_t)row * nwords + (v >> 5);
+    return bmprefix[o] + __popc(bm[o] & ((1u << (v & 31)) - 1u));
+}
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ int group_sum_int(int v) {
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif

@@ -1,0 +1,475 @@
+// A6-A12: projected gradient descent over the per-cycle weights (reference: DESC.m:148-261).
+//
+// One fused kernel per iteration.  A group of G lanes owns one edge l=(i,j) and keeps its
+// <= G*EPL slots in registers; for state t-1 -> t it
+//   * gathers S_{t-1}[e_jk], S_{t-1}[e_ki]                                   (DESC.m:193)
+//   * adds the partner sums A_l, B_l gated by the slot's appears flags        (DESC.m:189-193)
+//   * removes the edge's mean gradient ("Riemannian" projection)              (DESC.m:195-204)
+//   * takes the step-rule step                                                (DESC.m:207)
+//   * projects onto the probability simplex                                   (DESC.m:208-224)
+//   * writes w_t, S_t[l] = w.S0                                               (DESC.m:229)
+//   * scatters w_t into the partner-sum accumulators of state t (next iteration's A, B)
+//   * accumulates objective(state t-1) = sum w (S[e_jk]+S[e_ki]) and |S_t - S_{t-1}|  (DESC.m:232-233)
+//
+// Partner sums in scatter form: the reference's
+//   A_l = sum_{k: IKJ_appears} w(ik;j),  B_l = sum_{k: JKI_appears} w(jk;i)
+// are per-edge scalars; slot (ij;k) is the reciprocal of (ik;j) via vertex i and of (jk;i) via
+// vertex j, and the appears flags are symmetric, so slot c adds w_c to the "via shared vertex"
+// accumulator of each partner edge whose flag is set.  This needs no IKJ/JKI index arrays
+// (the partner edge ids are already streamed for the S gathers) and shards over GPUs with one
+// all-reduce of the 2m accumulators per iteration.
+//
+// The objective of state t is only known while running iteration t+1 (it needs all of S_t), so
+// the early-stop decision lags by one kernel; w and S are ping-ponged, and when the reference
+// would have stopped at iteration u the buffers of state u are still intact (later launches see
+// the `stopped` flag and return immediately).
+//
+// The simplex projection uses Michelot's active-set iteration: T <- (sum_{w>T} w - 1)/#{w>T}
+// until the active set stops shrinking.  It converges to the same threshold as the reference's
+// sort-and-scan (DESC.m:215-223) without sorting.
+#include "internal.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+struct PgdArgs {
+    const int64_t* rowptr;
+    const uint32_t *pk_jk, *pk_ki;
+    const double* S0;
+    const double* w_cur;
+    double* w_next;
+    const double* S_cur;
+    double* S_next;
+    const double* acc_cur;
+    double* acc_next;  // 2m + [obj, change]
+    double* adam_m;
+    double* adam_v;
+    const int* ctrl;   // [0] = stopped
+    int64_t e0, e1, slot_base, m;
+    double lr;         // effective step size of this iteration
+    double beta1, beta2, corr1, corr2;  // Adam
+};
+
+template <int G, int EPL, int RULE>
+__global__ void __launch_bounds__(256)
+k_pgd_iter(PgdArgs a) {
+    if (a.ctrl[0]) return;
+    const int r = threadIdx.x & (G - 1);
+    const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    const int64_t e = a.e0 + grp;
+    const bool valid = e < a.e1;
+    int64_t s0 = 0;
+    int ns = 0;
+    if (valid) {
+        s0 = a.rowptr[e];
+        ns = (int)(a.rowptr[e + 1] - s0);
+        s0 -= a.slot_base;
+    }
+    double objp = 0.0, chgp = 0.0;
+    double w[EPL], d[EPL];
+    uint32_t pj[EPL], pi[EPL];
+    double A = 0.0, B = 0.0;
+    if (ns > 0) {
+        A = a.acc_cur[2 * e];
+        B = a.acc_cur[2 * e + 1];
+    }
+    double gsum = 0.0;
+#pragma unroll
+    for (int x = 0; x < EPL; x++) {
+        const int idx = r + x * G;
+        w[x] = 0.0;
+        d[x] = 0.0;
+        pj[x] = pi[x] = 0u;
+        if (idx < ns) {
+            const int64_t s = s0 + idx;
+            w[x] = a.w_cur[s];
+            d[x] = a.S0[s];
+            pj[x] = a.pk_jk[s];
+            pi[x] = a.pk_ki[s];
+        }
+    }
+    double g[EPL];
+#pragma unroll
+    for (int x = 0; x < EPL; x++) {
+        g[x] = 0.0;
+        if (r + x * G < ns) {
+            const double sg = a.S_cur[pj[x] & PK_MASK] + a.S_cur[pi[x] & PK_MASK];
+            objp += w[x] * sg;
+            const double part = ((pi[x] & PK_APP) ? A : 0.0) + ((pj[x] & PK_APP) ? B : 0.0);
+            g[x] = sg + part * d[x];
+            gsum += g[x];
+        }
+    }
+    gsum = group_sum<G>(gsum);
+    const double gmean = ns > 0 ? gsum / (double)ns : 0.0;
+    // step
+    double wsum = 0.0;
+#pragma unroll
+    for (int x = 0; x < EPL; x++) {
+        if (r + x * G < ns) {
+            const double gr = g[x] - gmean;
+            double step;
+            if (RULE == 0) {
+                step = -a.lr * gr;
+            } else {
+                const int64_t s = s0 + r + x * G;
+                const double mt = a.beta1 * a.adam_m[s] + (1.0 - a.beta1) * gr;
+                const double vt = a.beta2 * a.adam_v[s] + (1.0 - a.beta2) * (gr * gr);
+                a.adam_m[s] = mt;
+                a.adam_v[s] = vt;
+                step = -a.lr * (mt / a.corr1) / (sqrt(vt / a.corr2) + 1e-8);
+            }
+            w[x] = w[x] + step;
+            wsum += w[x];
+        }
+    }
+    // Michelot projection onto the simplex
+    wsum = group_sum<G>(wsum);
+    int cnt = ns;
+    double T = ns > 0 ? (wsum - 1.0) / (double)ns : 0.0;
+    for (int mit = 0; mit < G * EPL + 2; mit++) {  // the active set shrinks every pass: <= ns passes
+        double s2 = 0.0;
+        int c2 = 0;
+#pragma unroll
+        for (int x = 0; x < EPL; x++) {
+            if (r + x * G < ns && w[x] > T) {
+                s2 += w[x];
+                c2++;
+            }
+        }
+        s2 = group_sum<G>(s2);
+        c2 = group_sum_int<G>(c2);
+        const bool changed = (c2 != cnt) && (c2 > 0);
+        if (changed) {
+            T = (s2 - 1.0) / (double)c2;
+            cnt = c2;
+        }
+        if (!__any_sync(0xffffffffu, changed)) break;
+    }
+    double snew = 0.0;
+#pragma unroll
+    for (int x = 0; x < EPL; x++) {
+        if (r + x * G < ns) {
+            const double wo = fmax(w[x] - T, 0.0);
+            w[x] = wo;
+            snew += wo * d[x];
+            a.w_next[s0 + r + x * G] = wo;
+            if (pi[x] & PK_APP) atomicAdd(&a.acc_next[2 * (int64_t)(pi[x] & PK_MASK) + ((pi[x] & PK_SEL) ? 0 : 1)], wo);
+            if (pj[x] & PK_APP) atomicAdd(&a.acc_next[2 * (int64_t)(pj[x] & PK_MASK) + ((pj[x] & PK_SEL) ? 0 : 1)], wo);
+        }
+    }
+    snew = group_sum<G>(snew);
+    if (ns > 0 && r == 0) {
+        a.S_next[e] = snew;
+        chgp = fabs(snew - a.S_cur[e]);
+    }
+    // block reduction of the two scalars -> one atomic pair per block
+    objp = group_sum<32>(objp);
+    chgp = group_sum<32>(chgp);
+    __shared__ double sh[2][8];
+    const int wid = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        sh[0][wid] = objp;
+        sh[1][wid] = chgp;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double o = 0.0, c = 0.0;
+        for (int x = 0; x < (int)(blockDim.x >> 5); x++) {
+            o += sh[0][x];
+            c += sh[1][x];
+        }
+        atomicAdd(&a.acc_next[2 * a.m], o);
+        atomicAdd(&a.acc_next[2 * a.m + 1], c);
+    }
+}
+
+// state 0: uniform weights, S = mean of the edge's S0, accumulators of state 0 (DESC.m:148-157)
+template <int G>
+__global__ void __launch_bounds__(256)
+k_pgd_init(PgdArgs a) {
+    const int r = threadIdx.x & (G - 1);
+    const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t grp0 = grp - ((threadIdx.x & 31) / G);  // first group of this warp: warp-uniform trip count
+    for (int64_t eb = a.e0 + grp0; eb < a.e1; eb += ngrp) {
+        const int64_t e = eb + ((threadIdx.x & 31) / G);
+        const bool valid = e < a.e1;
+        const int64_t s0 = valid ? a.rowptr[e] - a.slot_base : 0;
+        const int ns = valid ? (int)(a.rowptr[e + 1] - a.rowptr[e]) : 0;
+        const double w0 = ns > 0 ? 1.0 / (double)ns : 0.0;
+        double sn = 0.0;
+        for (int idx = r; idx < ns; idx += G) {
+            const int64_t s = s0 + idx;
+            a.w_next[s] = w0;
+            sn += w0 * a.S0[s];
+            const uint32_t pi = a.pk_ki[s], pj = a.pk_jk[s];
+            if (pi & PK_APP) atomicAdd(&a.acc_next[2 * (int64_t)(pi & PK_MASK) + ((pi & PK_SEL) ? 0 : 1)], w0);
+            if (pj & PK_APP) atomicAdd(&a.acc_next[2 * (int64_t)(pj & PK_MASK) + ((pj & PK_SEL) ? 0 : 1)], w0);
+        }
+        sn = group_sum<G>(sn);
+        if (r == 0 && ns > 0) a.S_next[e] = sn;
+    }
+}
+
+// objective of the final state when the loop ran out of iterations (no later kernel computes it)
+template <int G>
+__global__ void __launch_bounds__(256)
+k_pgd_obj(PgdArgs a) {
+    if (a.ctrl[0]) return;
+    const int r = threadIdx.x & (G - 1);
+    const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
+    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / G;
+    double objp = 0.0;
+    for (int64_t e = a.e0 + grp; e < a.e1; e += ngrp) {
+        const int64_t s0 = a.rowptr[e] - a.slot_base;
+        const int ns = (int)(a.rowptr[e + 1] - a.rowptr[e]);
+        for (int idx = r; idx < ns; idx += G) {
+            const int64_t s = s0 + idx;
+            objp += a.w_cur[s] * (a.S_cur[a.pk_jk[s] & PK_MASK] + a.S_cur[a.pk_ki[s] & PK_MASK]);
+        }
+    }
+    objp = group_sum<32>(objp);
+    __shared__ double sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = objp;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double o = 0.0;
+        for (int x = 0; x < (int)(blockDim.x >> 5); x++) o += sh[x];
+        atomicAdd(&a.acc_next[2 * a.m], o);
+    }
+}
+
+__global__ void k_fill_double(double* p, int64_t n, double v) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// Bookkeeping after iteration t (DESC.m:232-257), one thread.
+//   red = acc_next tail of kernel t: red[0] = objective(state t-1), red[1] = sum|S_t - S_{t-1}|
+//   ctrl: [0]=stopped [1]=final_iter [2]=misses ; ctrlf[0] = objective(state t-2)
+// last==1: red[0] is objective(state t) from k_pgd_obj (no change term).
+__global__ void k_pgd_finalize(const double* __restrict__ red, int t, int last, int64_t m,
+                               double tol, int patience, double* __restrict__ hist,
+                               int* __restrict__ ctrl, double* __restrict__ ctrlf) {
+    if (ctrl[0]) return;
+    if (last) {
+        hist[2 * (t - 1) + 1] = red[0];
+        ctrl[1] = t;
+        return;
+    }
+    hist[2 * (t - 1)] = red[1] / (double)m;
+    if (t >= 2) {
+        const int u = t - 1;  // iteration whose objective just became known
+        const double obj = red[0];
+        hist[2 * (u - 1) + 1] = obj;
+        if (u > 1 && ctrlf[0] - obj < tol) {
+            ctrl[2] += 1;
+            if (ctrl[2] >= patience) {
+                ctrl[0] = 1;
+                ctrl[1] = u;
+            }
+        } else {
+            ctrl[2] = 0;
+        }
+        ctrlf[0] = obj;
+    }
+}
+
+template <int G, int EPL>
+static int launch_iter(desc_b200_handle* h, const PgdArgs& a, int rule_kind) {
+    const int64_t ne = h->e_end - h->e_begin;
+    const int64_t threads = ne * G;
+    const unsigned grid = (unsigned)((threads + 255) / 256);
+    if (grid == 0) return DESC_B200_OK;
+    if (rule_kind == 0)
+        k_pgd_iter<G, EPL, 0><<<grid, 256, 0, h->stream>>>(a);
+    else
+        k_pgd_iter<G, EPL, 1><<<grid, 256, 0, h->stream>>>(a);
+    KERNEL_CHECK(h);
+    return DESC_B200_OK;
+}
+
+static int launch_iter_any(desc_b200_handle* h, const PgdArgs& a, int rule_kind) {
+    const int ns = h->max_ns;
+    if (ns <= 32) return launch_iter<8, 4>(h, a, rule_kind);
+    if (ns <= 64) return launch_iter<16, 4>(h, a, rule_kind);
+    if (ns <= 128) return launch_iter<32, 4>(h, a, rule_kind);
+    if (ns <= 256) return launch_iter<32, 8>(h, a, rule_kind);
+    if (ns <= 512) return launch_iter<32, 16>(h, a, rule_kind);
+    if (ns <= 1024) return launch_iter<32, 32>(h, a, rule_kind);
+    desc_set_error("an edge has %d slots; the fused PGD kernel supports at most 1024 per edge "
+                   "(lower n_sample)", ns);
+    return DESC_B200_ERR_LIMIT;
+}
+
+// step size of call number t (1-based count of GetStep calls on the rule object)
+static double step_size(const desc_b200_step_rule* r, int64_t t) {
+    switch (r->kind) {
+        case 0: return r->lr;
+        case 1: return r->lr / (std::trunc((double)t / r->decay_interval) + 1.0);
+        default:
+            if (r->strategy == 0) return r->lr;
+            return 100.0 * (r->lr / (std::trunc((double)t / r->decay_interval) + 1.0));
+    }
+}
+
+int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int* iters_run) {
+    if (!h->have_s0) {
+        desc_set_error("pgd before cycle_inconsistency");
+        return DESC_B200_ERR_STATE;
+    }
+    if (iters < 0 || !rule || rule->kind < 0 || rule->kind > 2) {
+        desc_set_error("bad iters / step rule");
+        return DESC_B200_ERR_ARG;
+    }
+    cudaStream_t st = h->stream;
+    const int64_t m = h->m;
+    const int64_t nacc = 2 * m + 2;
+    const bool adam = rule->kind == 2 && rule->strategy == 0;
+    for (int b = 0; b < 2; b++) {
+        if (!h->S[b]) CUDA_TRY(cudaMalloc(&h->S[b], m * sizeof(double)));
+        if (!h->acc[b]) CUDA_TRY(cudaMalloc(&h->acc[b], nacc * sizeof(double)));
+    }
+    if (!h->d_ctrl) {
+        CUDA_TRY(cudaMalloc(&h->d_ctrl, 4 * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&h->d_ctrl_f, 2 * sizeof(double)));
+        CUDA_TRY(cudaMallocHost(&h->h_ctrl, 4 * sizeof(int)));
+    }
+    if (h->hist_cap < iters + 1) {
+        cudaFree(h->d_hist);
+        h->d_hist = nullptr;
+        CUDA_TRY(cudaMalloc(&h->d_hist, (size_t)2 * (iters + 1) * sizeof(double)));
+        h->hist_cap = iters + 1;
+    }
+    if (adam) {
+        const size_t nb = (size_t)std::max<int64_t>(h->n_slots, 1) * sizeof(double);
+        if (!h->adam_m) CUDA_TRY(cudaMalloc(&h->adam_m, nb));
+        if (!h->adam_v) CUDA_TRY(cudaMalloc(&h->adam_v, nb));
+        if (rule->t == 0) {  // HybridGradient.m:24-27: state is zeroed on the first call only
+            CUDA_TRY(cudaMemsetAsync(h->adam_m, 0, nb, st));
+            CUDA_TRY(cudaMemsetAsync(h->adam_v, 0, nb, st));
+        }
+    }
+    CUDA_TRY(cudaMemsetAsync(h->d_ctrl, 0, 4 * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(h->d_ctrl_f, 0, 2 * sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(h->d_hist, 0, (size_t)2 * (iters + 1) * sizeof(double), st));
+    {
+        const unsigned gb = (unsigned)((m + 255) / 256);
+        k_fill_double<<<gb, 256, 0, st>>>(h->S[0], m, 1.0);  // S_vec = ones(1,m), DESC.m:148
+        KERNEL_CHECK(h);
+        k_fill_double<<<gb, 256, 0, st>>>(h->S[1], m, 1.0);
+        KERNEL_CHECK(h);
+    }
+    PgdArgs a;
+    a.rowptr = h->rowptr;
+    a.pk_jk = h->pk_jk;
+    a.pk_ki = h->pk_ki;
+    a.S0 = h->S0;
+    a.adam_m = h->adam_m;
+    a.adam_v = h->adam_v;
+    a.ctrl = h->d_ctrl;
+    a.e0 = h->e_begin;
+    a.e1 = h->e_end;
+    a.slot_base = h->slot_base;
+    a.m = m;
+    a.beta1 = rule->beta_1;
+    a.beta2 = rule->beta_2;
+    a.corr1 = a.corr2 = 1.0;
+    a.lr = 0.0;
+    const int launches0 = h->launches;
+    const int G = h->max_ns <= 32 ? 8 : (h->max_ns <= 64 ? 16 : 32);
+    const int aux_grid = DESC_SMS * 8;
+
+    // ---- state 0
+    CUDA_TRY(cudaMemsetAsync(h->acc[0], 0, nacc * sizeof(double), st));
+    a.w_cur = nullptr;
+    a.w_next = h->w[0];
+    a.S_cur = nullptr;
+    a.S_next = h->S[0];
+    a.acc_cur = nullptr;
+    a.acc_next = h->acc[0];
+    if (h->n_slots > 0) {
+        if (G == 8)
+            k_pgd_init<8><<<aux_grid, 256, 0, st>>>(a);
+        else if (G == 16)
+            k_pgd_init<16><<<aux_grid, 256, 0, st>>>(a);
+        else
+            k_pgd_init<32><<<aux_grid, 256, 0, st>>>(a);
+        KERNEL_CHECK(h);
+    }
+    if (h->world > 1) {
+        DESC_TRY(desc_allreduce_sum(h, h->acc[0], nacc));
+        DESC_TRY(desc_allgather_ranges(h, h->S[0], sizeof(double), h->shard_edges));
+    }
+
+    cudaEvent_t evk0 = h->ev2, evk1 = h->ev3;
+    CUDA_TRY(cudaEventRecord(evk0, st));
+    int t_done = 0;
+    bool stopped = false;
+    const int check_every = 8;
+    for (int t = 1; t <= iters && !stopped; t++) {
+        const int cur = (t - 1) & 1, nxt = t & 1;
+        CUDA_TRY(cudaMemsetAsync(h->acc[nxt], 0, nacc * sizeof(double), st));
+        a.w_cur = h->w[cur];
+        a.w_next = h->w[nxt];
+        a.S_cur = h->S[cur];
+        a.S_next = h->S[nxt];
+        a.acc_cur = h->acc[cur];
+        a.acc_next = h->acc[nxt];
+        const int64_t tcall = rule->t + t;
+        a.lr = step_size(rule, tcall);
+        if (adam) {
+            a.corr1 = 1.0 - std::pow(rule->beta_1, (double)tcall);
+            a.corr2 = 1.0 - std::pow(rule->beta_2, (double)tcall);
+        }
+        DESC_TRY(launch_iter_any(h, a, adam ? 1 : 0));
+        if (h->world > 1) {
+            DESC_TRY(desc_allreduce_sum(h, h->acc[nxt], nacc));
+            DESC_TRY(desc_allgather_ranges(h, h->S[nxt], sizeof(double), h->shard_edges));
+        }
+        k_pgd_finalize<<<1, 1, 0, st>>>(h->acc[nxt] + 2 * m, t, 0, m, 1e-5, 30, h->d_hist, h->d_ctrl, h->d_ctrl_f);
+        KERNEL_CHECK(h);
+        t_done = t;
+        if (t % check_every == 0 || t == iters) {
+            CUDA_TRY(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            stopped = h->h_ctrl[0] != 0;
+        }
+    }
+    CUDA_TRY(cudaEventRecord(evk1, st));
+    int final_iter = 0;
+    if (stopped) {
+        final_iter = h->h_ctrl[1];
+    } else if (iters > 0) {
+        // objective of the last state
+        const int cur = iters & 1, nxt = (iters + 1) & 1;
+        CUDA_TRY(cudaMemsetAsync(h->acc[nxt] + 2 * m, 0, 2 * sizeof(double), st));
+        a.w_cur = h->w[cur];
+        a.S_cur = h->S[cur];
+        a.acc_next = h->acc[nxt];
+        if (h->n_slots > 0) {
+            if (G == 8)
+                k_pgd_obj<8><<<aux_grid, 256, 0, st>>>(a);
+            else if (G == 16)
+                k_pgd_obj<16><<<aux_grid, 256, 0, st>>>(a);
+            else
+                k_pgd_obj<32><<<aux_grid, 256, 0, st>>>(a);
+            KERNEL_CHECK(h);
+        }
+        if (h->world > 1) DESC_TRY(desc_allreduce_sum(h, h->acc[nxt] + 2 * m, 2));
+        k_pgd_finalize<<<1, 1, 0, st>>>(h->acc[nxt] + 2 * m, iters, 1, m, 1e-5, 30, h->d_hist, h->d_ctrl, h->d_ctrl_f);
+        KERNEL_CHECK(h);
+        final_iter = iters;
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    h->final_buf = final_iter & 1;
+    h->have_pgd = true;
+    *iters_run = final_iter;
+    rule->t += final_iter;
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, evk0, evk1));
+    h->tm.pgd_launches = h->launches - launches0;
+    h->tm.pgd_iter_ms = t_done > 0 ? ms / t_done : 0.0;
+    return DESC_B200_OK;
+}

@@ -1,0 +1,339 @@
+"""Host-side mirror of the reference's solver interface, on top of the C ABI.
+
+Function names, argument meaning and outputs follow the reference's MATLAB functions:
+
+* ``DESC_PGD(Ind, RijMat, params)  -> S_vec``             Algorithms/DESC_PGD.m:14
+* ``DESC_init(Ind, RijMat, params) -> (R_est, S_vec)``    Algorithms/DESC_init.m:14
+* ``DESC(Ind, RijMat, params) -> (R_est, R_init, S_vec)`` Algorithms/DESC.m:14
+* ``GCW(Ind, AdjMat, RijMat, S_vec) -> R_est``            Utils/GCW.m:1
+* step rules ``ConstantStepSize``, ``PiecewiseStepSize``, ``HybridGradient``  (Utils/*.m)
+
+``Ind`` is the reference's m x 2, 1-based, i<j, (i,j)-sorted edge list; ``RijMat`` is
+3 x 3 x m; ``params`` is a dict with the reference's field names (``iters``, ``Gradient``,
+``make_plots``, ``ErrVec``, ``R_orig``; ``learning_rate`` is accepted and ignored exactly as
+in DESC.m:169).  Extra, optional keys that the reference cannot express: ``n_sample``
+(0 = reference rule), ``seed`` (sampler seed), ``cycles`` (explicit ``(ptr, apex)`` lists),
+``verbose`` (print the reference's per-iteration progress line, DESC.m:241).
+
+All arithmetic happens on the GPU inside ``libdesc_b200.so``.  Nothing here computes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DescError, StepRule, Timings, Opts
+
+
+# ---------------------------------------------------------------------------------------
+# Step rules: parameter holders with the reference's property names.  GetStep is evaluated
+# on the device inside the fused PGD kernel; the objects only carry state (``t``).
+# ---------------------------------------------------------------------------------------
+class ConstantStepSize:
+    """Utils/ConstantStepSize.m: ``step = -learning_rate * grad``."""
+
+    def __init__(self, learning_rate):
+        self.learning_rate = float(learning_rate)
+
+    def _to_c(self):
+        return StepRule(kind=0, strategy=0, lr=self.learning_rate, decay_interval=1.0, beta_1=0.0, beta_2=0.0, t=0)
+
+    def _from_c(self, r):
+        pass
+
+
+class PiecewiseStepSize:
+    """Utils/PiecewiseStepSize.m: ``t++; step = -lr/(fix(t/decay_interval)+1) * grad``."""
+
+    def __init__(self, learning_rate, decay_interval):
+        self.learning_rate = float(learning_rate)
+        self.decay_interval = float(decay_interval)
+        self.t = 0
+
+    def _to_c(self):
+        return StepRule(kind=1, strategy=0, lr=self.learning_rate, decay_interval=self.decay_interval,
+                        beta_1=0.0, beta_2=0.0, t=int(self.t))
+
+    def _from_c(self, r):
+        self.t = int(r.t)
+
+
+class HybridGradient:
+    """Utils/HybridGradient.m: Adam (strategy 0) or 100x decayed SGD (strategy 1, after ``stopAdam``).
+
+    The Adam moments ``m_t``/``v_t`` live on the device inside the solver handle (they are
+    m_cycle long); they are zeroed when ``t == 0`` as HybridGradient.m:24-27 does.
+    """
+
+    def __init__(self, lr, beta_1, beta_2, decay_interval):
+        self.lr, self.beta_1, self.beta_2 = float(lr), float(beta_1), float(beta_2)
+        self.decay_interval = float(decay_interval)
+        self.t = 0
+        self.strategy = 0
+
+    def stopAdam(self):
+        self.strategy = 1
+        return self
+
+    def _to_c(self):
+        return StepRule(kind=2, strategy=int(self.strategy), lr=self.lr, decay_interval=self.decay_interval,
+                        beta_1=self.beta_1, beta_2=self.beta_2, t=int(self.t))
+
+    def _from_c(self, r):
+        self.t = int(r.t)
+
+
+# ---------------------------------------------------------------------------------------
+# buffers
+# ---------------------------------------------------------------------------------------
+def _is_device(x):
+    return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
+
+
+def _host_f64(x, shape_check=None):
+    a = np.asfortranarray(np.asarray(x, dtype=np.float64))
+    if shape_check is not None:
+        shape_check(a)
+    return a
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(a.ctypes.data)
+
+
+class Solver:
+    """One graph on one GPU (or one rank of a multi-GPU solve): owns a ``desc_b200_handle``.
+
+    ``Ind``/``RijMat`` may be numpy arrays (copied to the device by the library) or CUDA torch
+    tensors already laid out like MATLAB memory (``Ind``: 2m doubles, all i then all j;
+    ``RijMat``: 9m doubles, element (r,c) of edge e at 9e+r+3c), in which case they are used
+    in place (``RijMat`` must outlive the solver).
+    """
+
+    def __init__(self, Ind, RijMat, n=0, device=-1, stream=None, rank=0, world=1, nccl_id=None):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self._keep = []
+        flags = 0
+        if _is_device(Ind) != _is_device(RijMat):
+            raise ValueError("Ind and RijMat must both be host arrays or both be CUDA tensors")
+        if _is_device(Ind):
+            flags |= _lib.INPUTS_ON_DEVICE
+            m = int(Ind.numel() // 2)
+            if Ind.numel() != 2 * m or RijMat.numel() != 9 * m or str(Ind.dtype) != "torch.float64" \
+                    or str(RijMat.dtype) != "torch.float64" or not Ind.is_contiguous() or not RijMat.is_contiguous():
+                raise ValueError("device inputs must be contiguous float64 with 2m and 9m elements")
+            ind_buf, r_buf = Ind, RijMat
+        else:
+            Ind = np.asarray(Ind)
+            if Ind.ndim != 2 or Ind.shape[1] != 2:
+                raise ValueError("Ind must be m x 2")
+            RijMat = np.asarray(RijMat)
+            if RijMat.ndim != 3 or RijMat.shape[:2] != (3, 3) or RijMat.shape[2] != Ind.shape[0]:
+                raise ValueError("RijMat must be 3 x 3 x m")
+            m = Ind.shape[0]
+            ind_buf, r_buf = _host_f64(Ind), _host_f64(RijMat)
+        self._keep += [ind_buf, r_buf]
+        idbuf = None
+        if world > 1:
+            idbuf = C.create_string_buffer(bytes(nccl_id), 128)
+            self._keep.append(idbuf)
+        opts = Opts(device=int(device), flags=flags, stream=C.c_void_p(stream) if stream else None,
+                    rank=int(rank), world=int(world), nccl_id=C.cast(idbuf, C.c_void_p) if idbuf else None)
+        _lib.check(self._lib.desc_b200_create(C.byref(self._h), int(n), int(m), _ptr(ind_buf), _ptr(r_buf),
+                                             C.byref(opts)))
+        self.m = m
+        self.rank, self.world = int(rank), int(world)
+
+    # -- lifetime ------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.desc_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- stages (DESC.m:19-263) ------------------------------------------------------------
+    def build_incidence(self, n_sample=0, seed=0, cycles=None):
+        ptr = apex = None
+        if cycles is not None:
+            ptr = np.ascontiguousarray(cycles[0], dtype=np.int64)
+            apex = np.ascontiguousarray(cycles[1], dtype=np.int32)
+            if ptr.size != self.m + 1 or apex.size != int(ptr[-1]):
+                raise ValueError("cycles=(ptr, apex): ptr needs m+1 entries and apex ptr[-1] entries")
+        _lib.check(self._lib.desc_b200_build_incidence(self._h, int(n_sample), int(seed) & (2 ** 64 - 1),
+                                                      _ptr(ptr), _ptr(apex)))
+        return self.info()
+
+    def cycle_inconsistency(self):
+        _lib.check(self._lib.desc_b200_cycle_inconsistency(self._h))
+
+    def pgd(self, iters, rule, want_S=True, want_hist=True):
+        iters = int(iters)
+        S = np.empty(self.m, dtype=np.float64) if want_S else None
+        hist = np.zeros((max(iters, 1), 2), dtype=np.float64) if want_hist else None
+        r = rule._to_c()
+        run = C.c_int32(0)
+        _lib.check(self._lib.desc_b200_pgd(self._h, iters, C.byref(r), _ptr(S), _ptr(hist), C.byref(run)))
+        rule._from_c(r)
+        k = int(run.value)
+        return S, (hist[:k] if hist is not None else None), k
+
+    def gcw(self, S_vec=None, want_R=True):
+        info = self.info()
+        S = None if S_vec is None else np.ascontiguousarray(np.asarray(S_vec, dtype=np.float64).ravel())
+        if S is not None and S.size != self.m:
+            raise ValueError("S_vec must have m entries")
+        R = np.empty((3, 3, info["n"]), dtype=np.float64, order="F") if want_R else None
+        _lib.check(self._lib.desc_b200_gcw(self._h, _ptr(S), _ptr(R)))
+        return R
+
+    # -- getters -------------------------------------------------------------------------
+    def info(self):
+        a = (C.c_int64 * 10)()
+        _lib.check(self._lib.desc_b200_get_info(self._h, a))
+        keys = ["n", "m", "m_pos", "m_cycle", "n_sample", "max_slots_per_edge", "edge_begin", "edge_end",
+                "local_slots", "max_codeg"]
+        return dict(zip(keys, [int(v) for v in a]))
+
+    def codeg(self):
+        out = np.empty(self.m, dtype=np.int32)
+        _lib.check(self._lib.desc_b200_get_codeg(self._h, _ptr(out)))
+        return out
+
+    def incidence(self):
+        info = self.info()
+        rowptr = np.empty(self.m + 1, dtype=np.int64)
+        apex = np.empty(info["m_cycle"], dtype=np.int32)
+        _lib.check(self._lib.desc_b200_get_incidence(self._h, _ptr(rowptr), _ptr(apex)))
+        return rowptr, apex
+
+    def slots(self):
+        ns = self.info()["local_slots"]
+        e_jk = np.empty(ns, dtype=np.int32)
+        e_ki = np.empty(ns, dtype=np.int32)
+        a = np.empty(ns, dtype=np.uint8)
+        b = np.empty(ns, dtype=np.uint8)
+        _lib.check(self._lib.desc_b200_get_slots(self._h, _ptr(e_jk), _ptr(e_ki), _ptr(a), _ptr(b)))
+        return e_jk, e_ki, a.astype(bool), b.astype(bool)
+
+    def S0(self):
+        out = np.empty(self.info()["local_slots"], dtype=np.float64)
+        _lib.check(self._lib.desc_b200_get_s0(self._h, _ptr(out)))
+        return out
+
+    def w(self):
+        out = np.empty(self.info()["local_slots"], dtype=np.float64)
+        _lib.check(self._lib.desc_b200_get_w(self._h, _ptr(out)))
+        return out
+
+    def gcw_info(self):
+        a = (C.c_double * 8)()
+        _lib.check(self._lib.desc_b200_get_gcw_info(self._h, a))
+        return {"iters": int(a[0]), "residual": float(a[1]), "theta": [float(a[2]), float(a[3]), float(a[4])]}
+
+    def timings(self):
+        t = Timings()
+        _lib.check(self._lib.desc_b200_get_timings(self._h, C.byref(t)))
+        return t.as_dict()
+
+    def sync(self):
+        _lib.check(self._lib.desc_b200_sync(self._h))
+
+
+def device_count():
+    n = _lib.load().desc_b200_device_count()
+    if n < 0:
+        _lib.check(n)
+    return n
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    _lib.check(_lib.load().desc_b200_nccl_unique_id(buf))
+    return buf.raw
+
+
+# ---------------------------------------------------------------------------------------
+# The reference's entry points
+# ---------------------------------------------------------------------------------------
+def _param(params, key, default=None):
+    if isinstance(params, dict):
+        return params.get(key, default)
+    return getattr(params, key, default)
+
+
+def _run_pgd(Ind, RijMat, params, want_gcw, **solver_kw):
+    rule = _param(params, "Gradient")
+    if rule is None or not hasattr(rule, "_to_c"):
+        raise ValueError("params.Gradient must be a ConstantStepSize / PiecewiseStepSize / HybridGradient object")
+    if _param(params, "make_plots", False):
+        raise NotImplementedError("params.make_plots=true (per-iteration GCW diagnostics and figures, "
+                                  "DESC.m:235-239,315-344) is not part of the device hot path")
+    iters = int(_param(params, "iters"))
+    s = Solver(Ind, RijMat, **solver_kw)
+    try:
+        s.build_incidence(n_sample=int(_param(params, "n_sample", 0) or 0), seed=int(_param(params, "seed", 0) or 0),
+                          cycles=_param(params, "cycles"))
+        s.cycle_inconsistency()
+        if _param(params, "verbose", False):
+            print("Initialization completed!")              # DESC.m:160
+            print("Reweighting Procedure Started ...")      # DESC.m:162
+        S_vec, hist, iters_run = s.pgd(iters, rule)
+        if _param(params, "verbose", False):
+            for t in range(iters_run):                       # DESC.m:241
+                print("iter %d: average change in S_vec %f, objective value: %f" % (t + 1, hist[t, 0], hist[t, 1]))
+        R = s.gcw() if want_gcw else None
+        extras = dict(hist=hist, iters_run=iters_run, info=s.info(), timings=s.timings())
+    finally:
+        s.close()
+    return S_vec.reshape(1, -1), R, extras
+
+
+def DESC_PGD(Ind, RijMat, params, **solver_kw):
+    """``[S_vec] = DESC_PGD(Ind, RijMat, params)`` (Algorithms/DESC_PGD.m:14).  S_vec is 1 x m."""
+    S_vec, _, _ = _run_pgd(Ind, RijMat, params, False, **solver_kw)
+    return S_vec
+
+
+def DESC_init(Ind, RijMat, params, **solver_kw):
+    """``[R_est, S_vec] = DESC_init(Ind, RijMat, params)`` (Algorithms/DESC_init.m:14)."""
+    S_vec, R, _ = _run_pgd(Ind, RijMat, params, True, **solver_kw)
+    return R, S_vec
+
+
+def DESC(Ind, RijMat, params, **solver_kw):
+    """``[R_est, R_init, S_vec] = DESC(Ind, RijMat, params)`` (Algorithms/DESC.m:14).
+
+    R_init and S_vec come from the device hot path (DESC.m:14-263).  The Lie-algebraic
+    refinement that turns R_init into R_est (DESC.m:265-312, Weighted_LAA) is SURVEY 8(f)
+    "next #1" and is not built yet: this function raises rather than return an unrefined R_est.
+    """
+    raise NotImplementedError("DESC(): the Weighted-LAA refinement stage (DESC.m:265-312) is not implemented on the "
+                              "device yet; use DESC_init for (R_init, S_vec) = DESC.m:14-263")
+
+
+def GCW(Ind, AdjMat, RijMat, S_vec, **solver_kw):
+    """``R_est = GCW(Ind, AdjMat, RijMat, S_vec)`` (Utils/GCW.m:1).  ``AdjMat`` is only a mask in the
+    reference (GCW.m:20) and is implied by ``Ind``; it is accepted and ignored."""
+    s = Solver(Ind, RijMat, **solver_kw)
+    try:
+        return s.gcw(S_vec)
+    finally:
+        s.close()

@@ -1,0 +1,169 @@
+/*
+ * desc_b200.h -- C ABI of the B200-native DESC solver hot path.
+ *
+ * This is the drop-in boundary.  The reference (ColeWyeth/DESC) has no FFI of its own: the
+ * boundary there is the MATLAB function signature
+ *
+ *     [R_est, R_init, S_vec] = DESC     (Ind, RijMat, params)   Algorithms/DESC.m:14
+ *     [S_vec]                = DESC_PGD (Ind, RijMat, params)   Algorithms/DESC_PGD.m:14
+ *     [R_est, S_vec]         = DESC_init(Ind, RijMat, params)   Algorithms/DESC_init.m:14
+ *     R_est                  = GCW(Ind, AdjMat, RijMat, S_vec)  Utils/GCW.m:1
+ *
+ * called from Demo/compare_algorithms.m:72.  The entry points below are what a MEX gateway
+ * (mex/desc_b200_mex.c) or any other FFI (ctypes: desc_b200/_lib.py) binds; every buffer in a
+ * signature is a plain pointer in MATLAB's own memory layout, so an mxArray's mxGetPr()
+ * pointer can be passed straight through:
+ *
+ *   Ind    : m x 2 double, column-major (all i, then all j), 1-based, i<j, rows sorted by
+ *            (i,j)                              (Models/Uniform_Topology.m:33-34, DESC.m:19-22)
+ *   RijMat : 3 x 3 x m double, column-major: element (r,c) of edge e at 9*e + r + 3*c
+ *                                               (Uniform_Topology.m:47-51, DESC.m:65)
+ *   S_vec  : 1 x m double, 1.0 for edges without 3-cycles   (DESC.m:148)
+ *   R_est  : 3 x 3 x n double, column-major                 (GCW.m:29)
+ *
+ * Every function returns DESC_B200_OK (0) or a negative error code; the message is available
+ * from desc_b200_last_error() (thread-local).  There is NO CPU fallback: without a CUDA
+ * device every call fails with DESC_B200_ERR_CUDA.
+ *
+ * All device memory is owned by the handle.  Host buffers are owned by the caller and are
+ * not referenced after the call returns (exception: create with DESC_B200_INPUTS_ON_DEVICE
+ * borrows the RijMat device buffer until destroy).
+ */
+#ifndef DESC_B200_H
+#define DESC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DESC_B200_VERSION 100
+
+#define DESC_B200_OK 0
+#define DESC_B200_ERR_ARG -1      /* bad argument / input violates the layout contract */
+#define DESC_B200_ERR_CUDA -2     /* CUDA runtime error, or no device */
+#define DESC_B200_ERR_STATE -3    /* stages called out of order */
+#define DESC_B200_ERR_LIMIT -4    /* problem exceeds a compiled-in limit */
+#define DESC_B200_ERR_NCCL -5     /* NCCL error */
+#define DESC_B200_ERR_NOCONV -6   /* spectral iteration did not converge */
+
+typedef struct desc_b200_handle desc_b200_handle;
+
+/* flags for desc_b200_opts.flags */
+#define DESC_B200_INPUTS_ON_DEVICE 1u /* Ind / RijMat passed to create are device pointers */
+
+typedef struct desc_b200_opts {
+    int32_t device;       /* CUDA device ordinal; -1 = current device                        */
+    uint32_t flags;
+    void* stream;         /* cudaStream_t to run on; NULL = the library creates its own      */
+    /* multi-GPU: one process per GPU.  world<=1 means single GPU.  nccl_id is the 128-byte
+       ncclUniqueId made by desc_b200_nccl_unique_id() on rank 0 and broadcast by the host. */
+    int32_t rank;
+    int32_t world;
+    const void* nccl_id;
+} desc_b200_opts;
+
+/* Step rules: params.Gradient of the reference (DESC.m:207).
+   kind 0: Utils/ConstantStepSize.m:9-11    step = -lr*grad
+   kind 1: Utils/PiecewiseStepSize.m:13-18  t++; step = -lr/(fix(t/decay_interval)+1)*grad
+   kind 2: Utils/HybridGradient.m:23-41     strategy 0: Adam(beta_1,beta_2,eps 1e-8, bias corrected)
+                                            strategy 1: step = -100*lr/(fix(t/decay_interval)+1)*grad
+   `t` is the object's call counter on entry; on return it has advanced by iters_run.       */
+typedef struct desc_b200_step_rule {
+    int32_t kind;
+    int32_t strategy;
+    double lr;
+    double decay_interval;
+    double beta_1;
+    double beta_2;
+    int64_t t;
+} desc_b200_step_rule;
+
+/* Stage timings in milliseconds (CUDA events on the library's stream), desc_b200_get_timings */
+typedef struct desc_b200_timings {
+    double h2d_ms;        /* create: host->device copies (0 with INPUTS_ON_DEVICE)           */
+    double graph_ms;      /* create: Ind conversion/validation + adjacency                   */
+    double build_ms;      /* build_incidence: co-degree, sampling, CSR incidence, flags      */
+    double cycle_ms;      /* cycle_inconsistency                                             */
+    double pgd_ms;        /* pgd: all iterations actually run                                */
+    double gcw_ms;        /* gcw: weights, power iteration, projection                       */
+    double d2h_ms;        /* device->host copies of results of the last pgd/gcw call         */
+    double pgd_iter_ms;   /* mean duration of one fused PGD iteration kernel                 */
+    int32_t pgd_launches; /* kernels launched by the last pgd call                           */
+    int32_t gcw_iters;    /* power iterations of the last gcw call                           */
+    int32_t total_launches; /* kernels launched by this handle so far                        */
+    int32_t reserved;
+} desc_b200_timings;
+
+const char* desc_b200_last_error(void);
+int desc_b200_version(void);
+/* number of visible CUDA devices, or a negative error code */
+int desc_b200_device_count(void);
+/* fills 128 bytes with a fresh ncclUniqueId (call on rank 0, broadcast, pass via opts) */
+int desc_b200_nccl_unique_id(void* out128);
+
+/* A1 (DESC.m:19-24): take the graph.  n may be 0 (= max(Ind(:)), as the reference does) or
+   an explicit node count >= max(Ind(:)).  Validates the layout contract (1<=i<j<=n,
+   strictly sorted rows, every node has an edge) and returns DESC_B200_ERR_ARG otherwise.   */
+int desc_b200_create(desc_b200_handle** out, int32_t n, int64_t m, const double* Ind,
+                     const double* RijMat, const desc_b200_opts* opts);
+void desc_b200_destroy(desc_b200_handle* h);
+
+/* A2-A4 (DESC.m:29-127): co-degrees, sampling budget, CSR edge->3-cycle incidence with
+   reciprocal-slot flags, all on device.
+   n_sample: 0 = reference rule max(ceil(median(codeg_pos)/4),30) (DESC.m:43); >0 = that
+   budget; <0 = keep every triangle.  An edge whose co-degree exceeds n_sample keeps the
+   n_sample common neighbours with the smallest desc_b200 sampler key (seed, edge, apex) --
+   the deterministic stand-in for datasample (DESC.m:84).
+   Explicit lists: cyc_ptr (m+1, host) / cyc_apex (cyc_ptr[m], host, 0-based) replace the
+   sampler (e.g. the lists a MATLAB run of the reference drew); pass NULL to sample.        */
+int desc_b200_build_incidence(desc_b200_handle* h, int32_t n_sample, uint64_t seed,
+                              const int64_t* cyc_ptr, const int32_t* cyc_apex);
+
+/* A5 (DESC.m:129-147): S0_long = abs(acos((trace(Rij*Rjk*Rki)-1)/2))/pi per slot, with the
+   reference's unfused operation order.                                                      */
+int desc_b200_cycle_inconsistency(desc_b200_handle* h);
+
+/* A6-A12 (DESC.m:148-261): initial weights + up to `iters` fused projected-gradient
+   iterations with the reference's early stop (30 consecutive objective decreases < 1e-5).
+   S_vec_out: m doubles (may be NULL).  hist_out: 2*iters doubles, row t = [average_change,
+   objective] of iteration t+1 (may be NULL).  iters_run_out: iterations executed.          */
+int desc_b200_pgd(desc_b200_handle* h, int32_t iters, desc_b200_step_rule* rule,
+                  double* S_vec_out, double* hist_out, int32_t* iters_run_out);
+
+/* A13 (Utils/GCW.m:1-38): weighted spectral recovery.  S_vec: m doubles on the host, or NULL
+   to use the result of the last desc_b200_pgd on this handle.  R_out: 9*n doubles.         */
+int desc_b200_gcw(desc_b200_handle* h, const double* S_vec, double* R_out);
+
+/* DESC_init.m:14 in one call: build + cycle + pgd + gcw (R_out may be NULL: DESC_PGD.m:14).*/
+int desc_b200_solve(desc_b200_handle* h, int32_t n_sample, uint64_t seed, int32_t iters,
+                    desc_b200_step_rule* rule, double* S_vec_out, double* R_out,
+                    double* hist_out, int32_t* iters_run_out);
+
+/* ---- getters (parity tests, MEX diagnostics) ---- */
+/* info[0]=n, [1]=m, [2]=m_pos, [3]=m_cycle (global), [4]=n_sample, [5]=max slots per edge,
+   [6]=first local edge, [7]=one-past-last local edge, [8]=local slot count, [9]=max co-degree */
+int desc_b200_get_info(desc_b200_handle* h, int64_t info[10]);
+/* co-degree of every edge (m int32) */
+int desc_b200_get_codeg(desc_b200_handle* h, int32_t* codeg);
+/* CSR incidence over ALL edges: rowptr (m+1 int64), apex (m_cycle int32, 0-based).  Any NULL skipped. */
+int desc_b200_get_incidence(desc_b200_handle* h, int64_t* rowptr, int32_t* apex);
+/* per LOCAL slot (all slots when world==1): e_jk / e_ki (0-based edge ids), appears flags
+   (IKJ_appears / JKI_appears, DESC.m:113,124) as bytes.  Any pointer may be NULL.           */
+int desc_b200_get_slots(desc_b200_handle* h, int32_t* e_jk, int32_t* e_ki, uint8_t* ikj_appears,
+                        uint8_t* jki_appears);
+/* S0_long and the final wijk of the LOCAL slots */
+int desc_b200_get_s0(desc_b200_handle* h, double* S0_long);
+int desc_b200_get_w(desc_b200_handle* h, double* wijk);
+/* last gcw call: info[0]=power iterations, [1]=final residual ||(N+I)/2 X - X H||_F,
+   [2..4]=the three Ritz values of D^-1/2 (W o R) D^-1/2 (= eigenvalues of GCW.m:27), descending */
+int desc_b200_get_gcw_info(desc_b200_handle* h, double info[8]);
+int desc_b200_get_timings(desc_b200_handle* h, desc_b200_timings* t);
+/* synchronise the handle's stream (for callers timing from outside) */
+int desc_b200_sync(desc_b200_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DESC_B200_H */

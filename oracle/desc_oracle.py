@@ -544,7 +544,7 @@ def pgd(inc: Incidence, S0, iters, rule, patience=30, tol=1e-5, verbose=False, r
 # --------------------------------------------------------------------------------------
 
 
-def gcw(Ind, RijMat, S_vec, dense_limit=1500):
+def gcw(Ind, RijMat, S_vec, dense_limit=400):
     """Top-3 eigenvectors ('la') of D^-1 (W o R), computed through the similar symmetric matrix
     D^-1/2 (W o R) D^-1/2, unit 2-norm columns, sign rule GCW.m:28, SVD projection :30-36."""
     n, ei, ej = check_ind(Ind)

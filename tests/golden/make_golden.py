@@ -1,0 +1,84 @@
+"""Generates the golden fixtures in this directory.  Run from the repo root:
+
+    python tests/golden/make_golden.py
+
+The reference (ColeWyeth/DESC) is MATLAB-only and ships no golden vectors, and no MATLAB/Octave
+exists in the build image, so these vectors are produced by ``oracle/desc_literal.py`` -- the
+loop-for-loop restatement of Algorithms/DESC.m:14-263 and Utils/GCW.m with the reference's dense
+data structures -- on graphs drawn by the restated generators (Models/Uniform_Topology.m,
+Models/Nonuniform_Topology.m).  PARITY UNPINNED against an execution of the real reference; the
+``.mat`` twin of every fixture lets a MATLAB user replay them through the real code (for the
+``nosample`` fixture, where datasample is never called, the real reference is deterministic).
+
+Each ``.npz`` holds the inputs (Ind, RijMat, R_orig, ErrVec, params) and the literal outputs
+(incidence arrays, S0_long, wijk, S_vec, hist, iters_run, R_est of GCW).
+"""
+import os
+import sys
+
+import numpy as np
+import scipy.io
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import desc_oracle as O          # noqa: E402
+from oracle.desc_literal import desc_literal  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+CASES = [
+    # name, generator, args, n_sample override (None = reference rule), sampler seed, rule, iters
+    ("uniform_n60_sigma0", "uniform", dict(n=60, p=0.5, q=0.2, sigma=0.0, model="uniform"), 10, 3,
+     ("const", 0.01), 100),
+    ("uniform_n70_noise", "uniform", dict(n=70, p=0.5, q=0.3, sigma=0.1, model="uniform"), 12, 5,
+     ("const", 0.01), 60),
+    ("uniform_n50_nosample", "uniform", dict(n=50, p=0.45, q=0.2, sigma=0.05, model="self-consistent"), None, 0,
+     ("const", 0.05), 40),
+    ("nonuniform_n64_adv", "nonuniform", dict(n=64, p=0.5, p_node_crpt=0.3, p_edge_crpt=0.5, sigma_in=0.05,
+                                               sigma_out=0.1, crpt_type="adv"), 9, 11, ("const", 1.0), 30),
+    ("uniform_n48_piecewise", "uniform", dict(n=48, p=0.6, q=0.25, sigma=0.02, model="uniform"), 8, 2,
+     ("piecewise", 0.05, 10), 45),
+    ("uniform_n48_adam", "uniform", dict(n=48, p=0.6, q=0.25, sigma=0.02, model="uniform"), 8, 2,
+     ("adam", 0.002, 0.9, 0.999, 20), 35),
+]
+
+
+def make_rule(spec):
+    if spec[0] == "const":
+        return O.ConstantStepSize(spec[1])
+    if spec[0] == "piecewise":
+        return O.PiecewiseStepSize(spec[1], spec[2])
+    return O.HybridGradient(spec[1], spec[2], spec[3], spec[4])
+
+
+def main():
+    for idx, (name, gen, args, ns, seed, rule_spec, iters) in enumerate(CASES):
+        rng = np.random.default_rng(1000 + idx)
+        a = dict(args)
+        n = a.pop("n")
+        if gen == "uniform":
+            mo = O.uniform_topology(n, a["p"], a["q"], a["sigma"], a["model"], rng=rng)
+        else:
+            mo = O.nonuniform_topology(n, a["p"], a["p_node_crpt"], a["p_edge_crpt"], a["sigma_in"],
+                                       a["sigma_out"], a["crpt_type"], rng=rng)
+        params = dict(iters=iters, Gradient=make_rule(rule_spec))
+        R_est, S_vec, ex = desc_literal(mo["Ind"], mo["RijMat"], params, seed=seed, n_sample=ns)
+        out = dict(
+            Ind=mo["Ind"], RijMat=mo["RijMat"], R_orig=mo["R_orig"], ErrVec=mo["ErrVec"],
+            n_sample_arg=np.int64(-1 if ns is None else ns), sampler_seed=np.int64(seed),
+            rule=np.array(rule_spec[1:], dtype=np.float64), rule_kind=np.str_(rule_spec[0]), iters=np.int64(iters),
+            n_sample=np.int64(ex["n_sample"]), cum_ind=ex["cum_ind"], CoDeg_pos_ind=ex["CoDeg_pos_ind"],
+            Ind_jk=ex["Ind_jk"], Ind_ki=ex["Ind_ki"], IJK=ex["IJK"], IKJ=ex["IKJ"], JKI=ex["JKI"],
+            S0_long=ex["S0_long"], wijk=ex["wijk"], S_vec=S_vec, hist=ex["hist"], iters_run=np.int64(ex["iters_run"]),
+            R_est=R_est)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        mat = {k: v for k, v in out.items() if k not in ("rule_kind",)}
+        mat["rule_kind"] = rule_spec[0]
+        scipy.io.savemat(os.path.join(HERE, name + ".mat"), mat, do_compression=True)
+        print("%-26s n=%d m=%d m_cycle=%d n_sample=%d iters_run=%d obj %.6g -> %.6g" % (
+            name, n, mo["Ind"].shape[0], ex["S0_long"].size, ex["n_sample"], ex["iters_run"], ex["hist"][0, 1],
+            ex["hist"][-1, 1]))
+
+
+if __name__ == "__main__":
+    main()
