@@ -7,18 +7,21 @@
 //   flip column 1 if det(V(1:3,:)) < 0                                  GCW.m:28
 //   R_i     = U diag(1,1,det(U V')) V' with [U,~,V] = svd(V_i)          GCW.m:30-36
 //
-// The reference forms the dense 3n x 3n matrix and calls eigs.  Here M is never formed: it is
-// similar to the symmetric N = D^-1/2 (W o R) D^-1/2, eigenvectors V = D^-1/2 U, and
-// the top-3 invariant subspace of N is found by block power (subspace) iteration on the shifted
-// operator (N + I)/2 -- spectrum in [0,1], order preserved, so "largest algebraic" is "largest
-// magnitude" -- with a block-sparse SpMV over the symmetric CSR adjacency built in build.cu:
+// The reference forms the dense 3n x 3n matrix and calls eigs (ARPACK).  Here M is never formed:
+// it is similar to the symmetric N = D^-1/2 (W o R) D^-1/2, eigenvectors
+// V = D^-1/2 U, and the three algebraically largest eigenpairs of N come from a thick-restarted
+// block Lanczos iteration (block size 3 = the multiplicity of the wanted cluster, full
+// re-orthogonalisation, Rayleigh-Ritz on the host over a <= 75-dimensional projected matrix)
+// driven by a block-sparse SpMV over the symmetric CSR adjacency built in build.cu:
 //
 //   y_i = sum_{p in row i}  c_e * (i<j ? R_e : R_e') * x_j ,   c_e = omega_e / sqrt(d_i d_j)
 //
 // One warp per node, lanes over the node's edges; node-centric so no atomics and a fixed
 // summation order (deterministic).  Each R_e is read twice per SpMV (once per endpoint).
-// The 3n x 3 block is re-orthonormalised by Cholesky-QR every step; all 3x3 algebra runs in
-// one-thread kernels so the loop needs no host round trip except the convergence poll.
+// All long-vector work (SpMV, block inner products, block updates, Cholesky-QR) runs on the
+// device with two-stage fixed-order reductions; only the tiny projected eigenproblem is solved
+// on the host.  Convergence is decided on the Lanczos residual estimate and then verified with
+// an explicitly computed residual || N X - X (X'NX) ||_F.
 #include "internal.cuh"
 
 #include <algorithm>
@@ -37,7 +40,8 @@
 #define SM_SGN 31   // 1: sign of column 1
 #define SM_THETA 32 // 3: Ritz values of N
 #define SM_FLAG 35  // 1: Cholesky breakdown flag
-#define SM_SIZE 40
+#define SM_R 36     // 9: R factor of the last Cholesky-QR (block = Q R)
+#define SM_SIZE 48
 
 __global__ void k_gcw_weights(const double* __restrict__ S, int64_t m, double* __restrict__ omega) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -70,7 +74,7 @@ __global__ void k_gcw_init(double* __restrict__ X, int64_t n9) {
     X[t] = (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
 }
 
-// Y[node] = 0.5 * (sum_p coef * op(R_e) * X[nbr] + X[node]) for node in [n0, n1)
+// Y[node] = sum_p coef * op(R_e) * X[nbr] for node in [n0, n1)
 __global__ void __launch_bounds__(256)
 k_gcw_spmv(const int* __restrict__ rowstart, const int* __restrict__ adj_nbr,
            const int* __restrict__ adj_eid, const double* __restrict__ Rij,
@@ -118,7 +122,7 @@ k_gcw_spmv(const int* __restrict__ rowstart, const int* __restrict__ adj_nbr,
 #pragma unroll
         for (int x = 0; x < 9; x++)
             if (lane == x) v = acc[x];
-        Y[9 * (int64_t)node + lane] = 0.5 * (v + X[9 * (int64_t)node + lane]);
+        Y[9 * (int64_t)node + lane] = v;
     }
 }
 
@@ -169,17 +173,18 @@ k_gcw_reduce(const double* __restrict__ X, const double* __restrict__ Y, int n,
     block_reduce_store<15>(v, partial + (size_t)blockIdx.x * GCW_NRED);
 }
 
-// one thread: H, G from partials; Cholesky of G; T = inv(L)'; also folds the residual partials
-// of the previous apply into small[SM_RES] and the history.
+// one thread: H, G from partials; Cholesky of G = L L'; T = inv(L)' (so Q = Y T), R = L' (Y = Q R).
+// accumulate != 0: R <- R_new * R_old (second Cholesky-QR pass).  A pivot that collapses relative
+// to the block's scale raises the breakdown flag (the block is numerically rank deficient).
 __global__ void k_gcw_small_orth(const double* __restrict__ partial, int nblocks,
-                                 double* __restrict__ small, double* __restrict__ res_hist, int it) {
-    double s[GCW_NRED];
-    for (int x = 0; x < GCW_NRED; x++) s[x] = 0.0;
+                                 double* __restrict__ small, int accumulate) {
+    double s[15];
+    for (int x = 0; x < 15; x++) s[x] = 0.0;
     for (int b = 0; b < nblocks; b++)
-        for (int x = 0; x < GCW_NRED; x++) s[x] += partial[(size_t)b * GCW_NRED + x];
+        for (int x = 0; x < 15; x++) s[x] += partial[(size_t)b * GCW_NRED + x];
     for (int x = 0; x < 9; x++) small[SM_H + x] = s[x];
     const double g00 = s[9], g01 = s[10], g02 = s[11], g11 = s[12], g12 = s[13], g22 = s[14];
-    // G = L L'
+    const double scale = fmax(g00, fmax(g11, g22));
     double l00 = sqrt(g00);
     double l10 = g01 / l00, l20 = g02 / l00;
     double d1 = g11 - l10 * l10;
@@ -187,17 +192,27 @@ __global__ void k_gcw_small_orth(const double* __restrict__ partial, int nblocks
     double l21 = (g12 - l20 * l10) / l11;
     double d2 = g22 - l20 * l20 - l21 * l21;
     double l22 = sqrt(d2);
-    if (!(g00 > 0.0) || !(d1 > 0.0) || !(d2 > 0.0)) small[SM_FLAG] = 1.0;
-    // Linv (lower)
+    const double thr = 1e-13 * scale;
+    if (!(scale > 1e-280) || !(g00 > thr) || !(d1 > thr) || !(d2 > thr)) small[SM_FLAG] = 1.0;
     double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
     double i10 = -l10 * i00 * i11;
     double i21 = -l21 * i11 * i22;
     double i20 = -(l20 * i00 + l21 * i10) * i22;
-    // T = Linv' (upper), column-major T[r + 3c]
     small[SM_T + 0] = i00; small[SM_T + 1] = 0.0; small[SM_T + 2] = 0.0;
     small[SM_T + 3] = i10; small[SM_T + 4] = i11; small[SM_T + 5] = 0.0;
     small[SM_T + 6] = i20; small[SM_T + 7] = i21; small[SM_T + 8] = i22;
-    if (it >= 0) res_hist[it] = 0.0;  // filled by k_gcw_small_res
+    // R = L' (upper), column-major
+    double Rn[9] = {l00, 0.0, 0.0, l10, l11, 0.0, l20, l21, l22};
+    if (accumulate) {
+        double Ro[9], Rt[9];
+        for (int x = 0; x < 9; x++) Ro[x] = small[SM_R + x];
+        for (int c = 0; c < 3; c++)
+            for (int r = 0; r < 3; r++)
+                Rt[r + 3 * c] = Rn[r] * Ro[3 * c] + Rn[r + 3] * Ro[1 + 3 * c] + Rn[r + 6] * Ro[2 + 3 * c];
+        for (int x = 0; x < 9; x++) small[SM_R + x] = Rt[x];
+    } else {
+        for (int x = 0; x < 9; x++) small[SM_R + x] = Rn[x];
+    }
 }
 
 // X_new[node] = Y[node] * T ; residual partial = sum || Y - X H ||^2
@@ -232,6 +247,33 @@ k_gcw_apply(double* __restrict__ X, const double* __restrict__ Y, int n,
             for (int r = 0; r < 3; r++)
                 X[9 * (int64_t)node + r + 3 * c] =
                     yb[r] * T[3 * c] + yb[r + 3] * T[1 + 3 * c] + yb[r + 6] * T[2 + 3 * c];
+    }
+    block_reduce_store<1>(v, partial + (size_t)blockIdx.x * GCW_NRED + 15);
+}
+
+// residual partial only: sum || Y - X H ||^2 with H = small[SM_H] (explicit verification)
+__global__ void __launch_bounds__(GCW_RED_TB)
+k_gcw_residual(const double* __restrict__ X, const double* __restrict__ Y, int n,
+               const double* __restrict__ small, double* __restrict__ partial) {
+    double H[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) H[q] = small[SM_H + q];
+    double v[1] = {0.0};
+    for (int node = blockIdx.x * blockDim.x + threadIdx.x; node < n; node += gridDim.x * blockDim.x) {
+        double xb[9], yb[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+            xb[q] = X[9 * (int64_t)node + q];
+            yb[q] = Y[9 * (int64_t)node + q];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const double xh = xb[r] * H[3 * c] + xb[r + 3] * H[1 + 3 * c] + xb[r + 6] * H[2 + 3 * c];
+                const double d = yb[r + 3 * c] - xh;
+                v[0] += d * d;
+            }
     }
     block_reduce_store<1>(v, partial + (size_t)blockIdx.x * GCW_NRED + 15);
 }
@@ -290,19 +332,6 @@ __device__ void jacobi_eig3(const double* A, double* evals, double* Z) {
         evals[c] = a[ord[c]][ord[c]];
         for (int r = 0; r < 3; r++) Z[r + 3 * c] = z[r][ord[c]];
     }
-}
-
-// Rayleigh-Ritz on H = X'(N+I)/2 X (from partials): Z, theta (of N)
-__global__ void k_gcw_small_ritz(const double* __restrict__ partial, int nblocks,
-                                 double* __restrict__ small) {
-    double s[9];
-    for (int x = 0; x < 9; x++) s[x] = 0.0;
-    for (int b = 0; b < nblocks; b++)
-        for (int x = 0; x < 9; x++) s[x] += partial[(size_t)b * GCW_NRED + x];
-    double ev[3], Z[9];
-    jacobi_eig3(s, ev, Z);
-    for (int x = 0; x < 9; x++) small[SM_Z + x] = Z[x];
-    for (int x = 0; x < 3; x++) small[SM_THETA + x] = 2.0 * ev[x] - 1.0;
 }
 
 // V[node] = isd[node] * X[node] * Z ; partial column sums of squares
@@ -437,6 +466,176 @@ __global__ void k_gcw_project(const double* __restrict__ V, const double* __rest
     for (int q = 0; q < 9; q++) R[9 * (int64_t)node + q] = out[q];
 }
 
+
+// ------------------------------------------------------------------------------------------
+// block Lanczos building blocks.  Basis blocks are stored back to back: block b at V + b*9n.
+// ------------------------------------------------------------------------------------------
+#define GCW_PROJ_BLOCKS 37   // x nb blocks of the basis; 4 resident CTAs per SM at nb >= 16
+#define GCW_DMAX 24          // processed basis blocks before a thick restart (72 columns)
+#define GCW_KEEP 2           // Ritz blocks kept at a restart (6 vectors)
+
+// partial[(b*gridDim.x + bx)*9 + a + 3c] = sum over nodes of V_b(:,a)' W(:,c)
+__global__ void __launch_bounds__(GCW_RED_TB)
+k_gcw_proj(const double* __restrict__ V, const double* __restrict__ W, int n, int64_t n9,
+           double* __restrict__ partial) {
+    const double* Vb = V + (size_t)blockIdx.y * n9;
+    double v[9];
+#pragma unroll
+    for (int x = 0; x < 9; x++) v[x] = 0.0;
+    for (int node = blockIdx.x * blockDim.x + threadIdx.x; node < n; node += gridDim.x * blockDim.x) {
+        double xb[9], yb[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+            xb[q] = Vb[9 * (int64_t)node + q];
+            yb[q] = W[9 * (int64_t)node + q];
+        }
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++)
+                v[a + 3 * b] += xb[3 * a] * yb[3 * b] + xb[3 * a + 1] * yb[3 * b + 1] + xb[3 * a + 2] * yb[3 * b + 2];
+    }
+    block_reduce_store<9>(v, partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 9);
+}
+
+// c[b*9 + q] = sum over bx of partial (fixed order); csum (+)= c
+__global__ void k_gcw_proj_finish(const double* __restrict__ partial, int nb, int nbx,
+                                  double* __restrict__ c, double* __restrict__ csum, int accumulate) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nb * 9) return;
+    const int b = t / 9, q = t % 9;
+    double s = 0.0;
+    for (int bx = 0; bx < nbx; bx++) s += partial[((size_t)b * nbx + bx) * 9 + q];
+    c[t] = s;
+    csum[t] = accumulate ? csum[t] + s : s;
+}
+
+// W -= sum_b V_b c_b
+__global__ void __launch_bounds__(256)
+k_gcw_subtract(const double* __restrict__ V, double* __restrict__ W, int n, int64_t n9, int nb,
+               const double* __restrict__ c) {
+    extern __shared__ double sc[];
+    for (int t = threadIdx.x; t < nb * 9; t += blockDim.x) sc[t] = c[t];
+    __syncthreads();
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= n) return;
+    double w[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) w[q] = W[9 * (int64_t)node + q];
+    for (int b = 0; b < nb; b++) {
+        const double* vb = V + (size_t)b * n9 + 9 * (int64_t)node;
+        const double* cb = sc + 9 * b;
+        double x[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) x[q] = vb[q];
+#pragma unroll
+        for (int col = 0; col < 3; col++)
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                w[r + 3 * col] -= x[r] * cb[3 * col] + x[r + 3] * cb[1 + 3 * col] + x[r + 6] * cb[2 + 3 * col];
+    }
+#pragma unroll
+    for (int q = 0; q < 9; q++) W[9 * (int64_t)node + q] = w[q];
+}
+
+// Out block o (blockIdx.y) = sum_b V_b * Z[b][o]   (Z: nb x nout blocks of 3x3, column-major 3x3)
+__global__ void __launch_bounds__(256)
+k_gcw_rotate(const double* __restrict__ V, double* __restrict__ Out, int n, int64_t n9, int nb,
+             int nout, const double* __restrict__ Z) {
+    extern __shared__ double sz[];
+    const int o = blockIdx.y;
+    for (int t = threadIdx.x; t < nb * 9; t += blockDim.x) sz[t] = Z[((size_t)(t / 9) * nout + o) * 9 + (t % 9)];
+    __syncthreads();
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= n) return;
+    double w[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) w[q] = 0.0;
+    for (int b = 0; b < nb; b++) {
+        const double* vb = V + (size_t)b * n9 + 9 * (int64_t)node;
+        const double* cb = sz + 9 * b;
+        double x[9];
+#pragma unroll
+        for (int q = 0; q < 9; q++) x[q] = vb[q];
+#pragma unroll
+        for (int col = 0; col < 3; col++)
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                w[r + 3 * col] += x[r] * cb[3 * col] + x[r + 3] * cb[1 + 3 * col] + x[r + 6] * cb[2 + 3 * col];
+    }
+#pragma unroll
+    for (int q = 0; q < 9; q++) Out[(size_t)o * n9 + 9 * (int64_t)node + q] = w[q];
+}
+
+__global__ void k_gcw_random(double* __restrict__ X, int64_t n9, uint64_t salt) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n9) return;
+    uint64_t z = desc_key(0x6a09e667f3bcc908ull + salt, (uint64_t)t, 7ull + salt);
+    X[t] = (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}
+
+// copy per-step results into the history the host reads at a Rayleigh-Ritz check
+__global__ void k_gcw_record(const double* __restrict__ csum, int nb, const double* __restrict__ small,
+                             double* __restrict__ hist_c, double* __restrict__ hist_r) {
+    const int t = threadIdx.x;
+    for (int x = t; x < nb * 9; x += blockDim.x) hist_c[x] = csum[x];
+    if (t < 9) hist_r[t] = small[SM_R + t];
+    if (t == 9) hist_r[9] = small[SM_FLAG];
+}
+
+// symmetric eigen-decomposition (cyclic Jacobi) of a small dense matrix on the host; eigenvalues
+// descending.  A is d x d column-major (destroyed), Z gets the eigenvectors as columns.
+static void host_jacobi_eig(std::vector<double>& A, int d, std::vector<double>& ev, std::vector<double>& Z) {
+    Z.assign((size_t)d * d, 0.0);
+    for (int i = 0; i < d; i++) Z[i + (size_t)i * d] = 1.0;
+    for (int i = 0; i < d; i++)
+        for (int j = i + 1; j < d; j++) {
+            const double v = 0.5 * (A[i + (size_t)j * d] + A[j + (size_t)i * d]);
+            A[i + (size_t)j * d] = A[j + (size_t)i * d] = v;
+        }
+    for (int sweep = 0; sweep < 100; sweep++) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < d; i++) {
+            diag += A[i + (size_t)i * d] * A[i + (size_t)i * d];
+            for (int j = i + 1; j < d; j++) off += A[i + (size_t)j * d] * A[i + (size_t)j * d];
+        }
+        if (off <= 1e-34 * (diag + 1e-300)) break;
+        for (int p = 0; p < d - 1; p++)
+            for (int q = p + 1; q < d; q++) {
+                const double apq = A[p + (size_t)q * d];
+                if (apq == 0.0) continue;
+                const double theta = (A[q + (size_t)q * d] - A[p + (size_t)p * d]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < d; k++) {
+                    const double akp = A[k + (size_t)p * d], akq = A[k + (size_t)q * d];
+                    A[k + (size_t)p * d] = c * akp - s * akq;
+                    A[k + (size_t)q * d] = s * akp + c * akq;
+                }
+                for (int k = 0; k < d; k++) {
+                    const double apk = A[p + (size_t)k * d], aqk = A[q + (size_t)k * d];
+                    A[p + (size_t)k * d] = c * apk - s * aqk;
+                    A[q + (size_t)k * d] = s * apk + c * aqk;
+                }
+                for (int k = 0; k < d; k++) {
+                    const double zkp = Z[k + (size_t)p * d], zkq = Z[k + (size_t)q * d];
+                    Z[k + (size_t)p * d] = c * zkp - s * zkq;
+                    Z[k + (size_t)q * d] = s * zkp + c * zkq;
+                }
+            }
+    }
+    std::vector<int> ord(d);
+    for (int i = 0; i < d; i++) ord[i] = i;
+    std::sort(ord.begin(), ord.end(), [&](int a, int b) { return A[a + (size_t)a * d] > A[b + (size_t)b * d]; });
+    ev.resize(d);
+    std::vector<double> Zs((size_t)d * d);
+    for (int c = 0; c < d; c++) {
+        ev[c] = A[ord[c] + (size_t)ord[c] * d];
+        for (int r = 0; r < d; r++) Zs[r + (size_t)c * d] = Z[r + (size_t)ord[c] * d];
+    }
+    Z.swap(Zs);
+}
+
 // node ranges balanced by adjacency entries
 static void node_bounds(desc_b200_handle* h, const std::vector<int>& rowstart, std::vector<int64_t>& nb) {
     const int n = h->n;
@@ -451,121 +650,313 @@ static void node_bounds(desc_b200_handle* h, const std::vector<int>& rowstart, s
     }
 }
 
+namespace {
+struct Lanczos {
+    desc_b200_handle* h;
+    int n;
+    int64_t n9;
+    int n0, n1;
+    std::vector<int64_t> nb9;
+    double* V;       // (GCW_DMAX + 2 + GCW_KEEP + 1) blocks
+    double* partial; // proj partials
+    double* c;       // 9 * (GCW_DMAX+1)
+    double* csum;
+    double* hist_c;  // per step: 9*(GCW_DMAX+1)
+    double* hist_r;  // per step: 16
+    double* Zdev;    // rotation coefficients
+    double* host;    // pinned staging
+
+    double* blk(int b) const { return V + (size_t)b * n9; }
+
+    int spmv(const double* X, double* Y) {
+        const unsigned grid = (unsigned)((((int64_t)(n1 - n0)) * 32 + 255) / 256);
+        if (grid > 0) {
+            k_gcw_spmv<<<grid, 256, 0, h->stream>>>(h->rowstart, h->adj_nbr, h->adj_eid, h->Rij, h->gcw_coef, X, Y, n0, n1);
+            KERNEL_CHECK(h);
+        }
+        DESC_TRY(desc_allgather_ranges(h, Y, sizeof(double), nb9));
+        return DESC_B200_OK;
+    }
+    // W (block index w) orthogonalised against blocks [0, nb): two passes, csum = total coefficients
+    int orth_against(int nb, int w) {
+        if (nb <= 0) return DESC_B200_OK;
+        for (int pass = 0; pass < 2; pass++) {
+            dim3 g(GCW_PROJ_BLOCKS, nb);
+            k_gcw_proj<<<g, GCW_RED_TB, 0, h->stream>>>(V, blk(w), n, n9, partial);
+            KERNEL_CHECK(h);
+            k_gcw_proj_finish<<<(nb * 9 + 127) / 128, 128, 0, h->stream>>>(partial, nb, GCW_PROJ_BLOCKS, c, csum, pass);
+            KERNEL_CHECK(h);
+            k_gcw_subtract<<<(n + 255) / 256, 256, nb * 9 * sizeof(double), h->stream>>>(V, blk(w), n, n9, nb, c);
+            KERNEL_CHECK(h);
+        }
+        return DESC_B200_OK;
+    }
+    // Cholesky-QR twice in place on block w; small[SM_R] = R, small[SM_FLAG] set on breakdown
+    int cholqr2(int w) {
+        for (int pass = 0; pass < 2; pass++) {
+            k_gcw_reduce<<<GCW_RED_BLOCKS, GCW_RED_TB, 0, h->stream>>>(blk(w), blk(w), n, h->gcw_red);
+            KERNEL_CHECK(h);
+            k_gcw_small_orth<<<1, 1, 0, h->stream>>>(h->gcw_red, GCW_RED_BLOCKS, h->gcw_small, pass);
+            KERNEL_CHECK(h);
+            k_gcw_apply<<<GCW_RED_BLOCKS, GCW_RED_TB, 0, h->stream>>>(blk(w), blk(w), n, h->gcw_small, h->gcw_red);
+            KERNEL_CHECK(h);
+        }
+        return DESC_B200_OK;
+    }
+    int random_block(int w, int nb, uint64_t salt) {
+        k_gcw_random<<<(unsigned)((n9 + 255) / 256), 256, 0, h->stream>>>(blk(w), n9, salt);
+        KERNEL_CHECK(h);
+        DESC_TRY(orth_against(nb, w));
+        CUDA_TRY(cudaMemsetAsync(h->gcw_small + SM_FLAG, 0, sizeof(double), h->stream));
+        DESC_TRY(cholqr2(w));
+        return DESC_B200_OK;
+    }
+};
+}  // namespace
+
+// k_gcw_apply reads X and Y separately; with X == Y (in-place Cholesky-QR) the residual partial is
+// meaningless and ignored.
+
 int desc_gcw_impl(desc_b200_handle* h, const double* d_S) {
     const int n = h->n;
     const int64_t m = h->m;
     const int64_t n9 = 9 * (int64_t)n;
     cudaStream_t st = h->stream;
+    // basis capacity: at most n blocks exist in a 3n-dimensional space
+    const int dmax = std::max(1, std::min(GCW_DMAX, n - 1));
+    const int keep = std::max(1, std::min(GCW_KEEP, dmax - 1));
+    const int total_blocks = GCW_DMAX + 2 + GCW_KEEP + 1;
+    const int hist_stride = 9 * (GCW_DMAX + 2);
     if (!h->omega) {
         CUDA_TRY(cudaMalloc(&h->omega, m * sizeof(double)));
         CUDA_TRY(cudaMalloc(&h->gcw_coef, m * sizeof(double)));
         CUDA_TRY(cudaMalloc(&h->isd, (size_t)n * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&h->X[0], n9 * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->X[0], (size_t)total_blocks * n9 * sizeof(double)));
         CUDA_TRY(cudaMalloc(&h->X[1], n9 * sizeof(double)));
         CUDA_TRY(cudaMalloc(&h->R_est, n9 * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&h->gcw_red, (size_t)GCW_RED_BLOCKS * GCW_NRED * sizeof(double)));
+        const size_t red = std::max<size_t>((size_t)GCW_RED_BLOCKS * GCW_NRED, (size_t)GCW_PROJ_BLOCKS * 9 * (GCW_DMAX + 2));
+        CUDA_TRY(cudaMalloc(&h->gcw_red, 2 * red * sizeof(double)));
         CUDA_TRY(cudaMalloc(&h->gcw_small, SM_SIZE * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&h->gcw_res, (size_t)(DESC_GCW_MAXIT + 8) * sizeof(double)));
-        CUDA_TRY(cudaMallocHost(&h->gcw_res_host, (size_t)(DESC_GCW_MAXIT + 8) * sizeof(double)));
+        // c | csum | hist_c[(DMAX+2) steps] | hist_r[(DMAX+2) steps x 16] | Z
+        const size_t work = (size_t)2 * hist_stride + (size_t)(GCW_DMAX + 2) * hist_stride + (size_t)(GCW_DMAX + 2) * 16 +
+                            (size_t)9 * (GCW_DMAX + 2) * (GCW_KEEP + 1) + 64;
+        CUDA_TRY(cudaMalloc(&h->gcw_res, work * sizeof(double)));
+        CUDA_TRY(cudaMallocHost(&h->gcw_res_host, work * sizeof(double)));
     }
-    std::vector<int64_t> nb(h->world + 1, 0);
-    nb[h->world] = n;
+    std::vector<int64_t> nbd(h->world + 1, 0);
+    nbd[h->world] = n;
     if (h->world > 1) {
         std::vector<int> rs(n + 1);
         CUDA_TRY(cudaMemcpyAsync(rs.data(), h->rowstart, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        node_bounds(h, rs, nb);
+        node_bounds(h, rs, nbd);
     }
-    std::vector<int64_t> nb9(nb);
-    for (auto& v : nb9) v *= 9;
-    const int n0 = (int)nb[h->rank], n1 = (int)nb[h->rank + 1];
+    Lanczos L;
+    L.h = h;
+    L.n = n;
+    L.n9 = n9;
+    L.n0 = (int)nbd[h->rank];
+    L.n1 = (int)nbd[h->rank + 1];
+    L.nb9 = nbd;
+    for (auto& v : L.nb9) v *= 9;
+    L.V = h->X[0];
+    const size_t red = std::max<size_t>((size_t)GCW_RED_BLOCKS * GCW_NRED, (size_t)GCW_PROJ_BLOCKS * 9 * (GCW_DMAX + 2));
+    L.partial = h->gcw_red + red;
+    L.c = h->gcw_res;
+    L.csum = L.c + hist_stride;
+    L.hist_c = L.csum + hist_stride;
+    L.hist_r = L.hist_c + (size_t)(GCW_DMAX + 2) * hist_stride;
+    L.Zdev = L.hist_r + (size_t)(GCW_DMAX + 2) * 16;
+    L.host = h->gcw_res_host;
+    double* host_hist_c = L.host + (L.hist_c - h->gcw_res);
+    double* host_hist_r = L.host + (L.hist_r - h->gcw_res);
+    double* host_Z = L.host + (L.Zdev - h->gcw_res);
 
     const unsigned gbm = (unsigned)((m + 255) / 256);
     CUDA_TRY(cudaMemsetAsync(h->gcw_small, 0, SM_SIZE * sizeof(double), st));
-    CUDA_TRY(cudaMemsetAsync(h->gcw_red, 0, (size_t)GCW_RED_BLOCKS * GCW_NRED * sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(h->gcw_red, 0, 2 * red * sizeof(double), st));
     k_gcw_weights<<<gbm, 256, 0, st>>>(d_S, m, h->omega);
     KERNEL_CHECK(h);
     k_gcw_degree<<<(unsigned)(((int64_t)n * 32 + 255) / 256), 256, 0, st>>>(h->rowstart, h->adj_eid, h->omega, n, h->isd);
     KERNEL_CHECK(h);
     k_gcw_coef<<<gbm, 256, 0, st>>>(h->ei, h->ej, h->omega, h->isd, m, h->gcw_coef);
     KERNEL_CHECK(h);
-    double* X = h->X[0];
-    double* Y = h->X[1];
-    k_gcw_init<<<(unsigned)((n9 + 255) / 256), 256, 0, st>>>(X, n9);
-    KERNEL_CHECK(h);
-    // orthonormalise the start block (Cholesky-QR twice)
-    for (int rep = 0; rep < 2; rep++) {
-        CUDA_TRY(cudaMemcpyAsync(Y, X, n9 * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        k_gcw_reduce<<<GCW_RED_BLOCKS, GCW_RED_TB, 0, st>>>(X, Y, n, h->gcw_red);
+
+    // projected matrix on the host: Hm is (3*cap) x (3*cap), column-major
+    const int cap = GCW_DMAX + 2;
+    const int ld = 3 * cap;
+    std::vector<double> Hm((size_t)ld * ld, 0.0);
+    auto Hset = [&](int r, int c, double v) { Hm[r + (size_t)c * ld] = v; Hm[c + (size_t)r * ld] = v; };
+
+    uint64_t salt = 1;
+    DESC_TRY(L.random_block(0, 0, salt++));
+    int nproc = 0;        // processed blocks: H columns known for blocks [0, nproc)
+    int nblk = 1;         // blocks in the basis (nproc processed + 1 pending, unless exhausted)
+    int steps_since_check = 0, first_step_of_batch = 0, total_spmv = 0;
+    bool trust_estimate = true, converged = false, exhausted = false;
+    double est = INFINITY, explicit_res = INFINITY;
+    std::vector<double> Rlast(9, 0.0);
+    std::vector<double> ev, Z;
+    const double tol = 2e-13, accept = 2e-11;
+    const int max_spmv = 6000;
+    int restarts = 0;
+
+    while (!converged && total_spmv < max_spmv) {
+        // ---- one Lanczos step: process the pending block (index nproc), create block nblk
+        const int p = nproc;
+        DESC_TRY(L.spmv(L.blk(p), L.blk(nblk)));
+        total_spmv++;
+        DESC_TRY(L.orth_against(nblk, nblk));
+        CUDA_TRY(cudaMemsetAsync(h->gcw_small + SM_FLAG, 0, sizeof(double), st));
+        DESC_TRY(L.cholqr2(nblk));
+        k_gcw_record<<<1, 128, 0, st>>>(L.csum, nblk, h->gcw_small, L.hist_c + (size_t)steps_since_check * hist_stride,
+                                        L.hist_r + (size_t)steps_since_check * 16);
         KERNEL_CHECK(h);
-        k_gcw_small_orth<<<1, 1, 0, st>>>(h->gcw_red, GCW_RED_BLOCKS, h->gcw_small, h->gcw_res, -1);
-        KERNEL_CHECK(h);
-        k_gcw_apply<<<GCW_RED_BLOCKS, GCW_RED_TB, 0, st>>>(X, Y, n, h->gcw_small, h->gcw_red);
-        KERNEL_CHECK(h);
-    }
-    const unsigned spmv_grid = (unsigned)((((int64_t)(n1 - n0)) * 32 + 255) / 256);
-    const double tol = 1e-13;
-    const int poll = 4;
-    int it = 0;
-    bool converged = false;
-    double last_res = INFINITY;
-    while (it < DESC_GCW_MAXIT && !converged) {
-        if (spmv_grid > 0) {
-            k_gcw_spmv<<<spmv_grid, 256, 0, st>>>(h->rowstart, h->adj_nbr, h->adj_eid, h->Rij, h->gcw_coef, X, Y, n0, n1);
+        if (steps_since_check == 0) first_step_of_batch = p;
+        steps_since_check++;
+        nproc++;
+        nblk++;
+        const bool full = nproc >= dmax;
+        const bool check = full || steps_since_check >= 4 || nblk > n;
+        if (!check) continue;
+
+        // ---- pull the step results, extend H, Rayleigh-Ritz on the host
+        CUDA_TRY(cudaMemcpyAsync(host_hist_c, L.hist_c, (size_t)steps_since_check * hist_stride * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(host_hist_r, L.hist_r, (size_t)steps_since_check * 16 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        bool breakdown = false;
+        int good_steps = steps_since_check;
+        for (int s = 0; s < steps_since_check && !breakdown; s++) {
+            const int pb = first_step_of_batch + s;      // block processed in this step
+            const double* cs = host_hist_c + (size_t)s * hist_stride;
+            for (int b = 0; b <= pb; b++)
+                for (int cc = 0; cc < 3; cc++)
+                    for (int a = 0; a < 3; a++) {
+                        const double v = cs[9 * b + a + 3 * cc];
+                        if (!(v == v)) {
+                            desc_set_error("GCW: non-finite value in the Lanczos recurrence (non-finite S_vec or RijMat?)");
+                            return DESC_B200_ERR_NOCONV;
+                        }
+                        if (b == pb) Hset(3 * b + a, 3 * pb + cc, 0.5 * (v + cs[9 * b + cc + 3 * a]));
+                        else Hset(3 * b + a, 3 * pb + cc, v);
+                    }
+            const double* hr = host_hist_r + (size_t)s * 16;
+            for (int x = 0; x < 9; x++) Rlast[x] = hr[x];
+            if (hr[9] != 0.0) {
+                breakdown = true;     // the block created in this step is numerically rank deficient;
+                good_steps = s + 1;   // later steps of the batch built on it and are dropped
+            }
+        }
+        if (breakdown) {
+            // keep the blocks processed up to and including the breakdown step; replace the unusable
+            // new block with a fresh random one (or stop if the whole space is spanned)
+            nproc = first_step_of_batch + good_steps;
+            nblk = nproc;
+            std::fill(Rlast.begin(), Rlast.end(), 0.0);
+            trust_estimate = false;
+            if (nblk >= n) exhausted = true;
+        }
+        steps_since_check = 0;
+        const int d = 3 * nproc;
+        std::vector<double> A((size_t)d * d);
+        for (int cc = 0; cc < d; cc++)
+            for (int r = 0; r < d; r++) A[r + (size_t)cc * d] = Hm[r + (size_t)cc * ld];
+        host_jacobi_eig(A, d, ev, Z);
+        est = 0.0;
+        for (int i = 0; i < 3 && i < d; i++) {
+            double rn = 0.0;
+            for (int r = 0; r < 3; r++) {
+                double v = 0.0;
+                for (int k = 0; k < 3; k++) v += Rlast[r + 3 * k] * Z[(d - 3 + k) + (size_t)i * d];
+                rn += v * v;
+            }
+            est = std::max(est, std::sqrt(rn));
+        }
+        const bool must_restart = full || breakdown || exhausted;
+        const bool verify_now = exhausted || (trust_estimate ? est <= tol : must_restart);
+        if (!verify_now && !must_restart) continue;
+
+        // ---- rotate to Ritz blocks: top `kr` blocks into the scratch area
+        const int kr = std::min(keep, nproc);
+        const int scratch = GCW_DMAX + 2;   // first scratch block
+        for (int b = 0; b < nproc; b++)
+            for (int o = 0; o < kr; o++)
+                for (int cc = 0; cc < 3; cc++)
+                    for (int r = 0; r < 3; r++)
+                        host_Z[((size_t)b * kr + o) * 9 + r + 3 * cc] = Z[(3 * b + r) + (size_t)(3 * o + cc) * d];
+        CUDA_TRY(cudaMemcpyAsync(L.Zdev, host_Z, (size_t)nproc * kr * 9 * sizeof(double), cudaMemcpyHostToDevice, st));
+        {
+            dim3 g((n + 255) / 256, kr);
+            k_gcw_rotate<<<g, 256, nproc * 9 * sizeof(double), st>>>(L.V, L.blk(scratch), n, n9, nproc, kr, L.Zdev);
             KERNEL_CHECK(h);
         }
-        DESC_TRY(desc_allgather_ranges(h, Y, sizeof(double), nb9));
-        k_gcw_reduce<<<GCW_RED_BLOCKS, GCW_RED_TB, 0, st>>>(X, Y, n, h->gcw_red);
-        KERNEL_CHECK(h);
-        k_gcw_small_orth<<<1, 1, 0, st>>>(h->gcw_red, GCW_RED_BLOCKS, h->gcw_small, h->gcw_res, it);
-        KERNEL_CHECK(h);
-        k_gcw_apply<<<GCW_RED_BLOCKS, GCW_RED_TB, 0, st>>>(X, Y, n, h->gcw_small, h->gcw_red);
-        KERNEL_CHECK(h);
-        k_gcw_small_res<<<1, 1, 0, st>>>(h->gcw_red, GCW_RED_BLOCKS, h->gcw_small, h->gcw_res, it);
-        KERNEL_CHECK(h);
-        it++;
-        if (it % poll == 0 || it == DESC_GCW_MAXIT) {
-            CUDA_TRY(cudaMemcpyAsync(h->gcw_res_host, h->gcw_res, (size_t)it * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (verify_now) {
+            // explicit verification on the three leading Ritz vectors: Y = N X, H3 = X'Y, ||Y - X H3||_F
+            double* X = L.blk(scratch);
+            double* Y = h->X[1];
+            DESC_TRY(L.spmv(X, Y));
+            total_spmv++;
+            k_gcw_reduce<<<GCW_RED_BLOCKS, GCW_RED_TB, 0, st>>>(X, Y, n, h->gcw_red);
+            KERNEL_CHECK(h);
+            k_gcw_small_orth<<<1, 1, 0, st>>>(h->gcw_red, GCW_RED_BLOCKS, h->gcw_small, 0);
+            KERNEL_CHECK(h);
+            k_gcw_residual<<<GCW_RED_BLOCKS, GCW_RED_TB, 0, st>>>(X, Y, n, h->gcw_small, h->gcw_red);
+            KERNEL_CHECK(h);
+            k_gcw_small_res<<<1, 1, 0, st>>>(h->gcw_red, GCW_RED_BLOCKS, h->gcw_small, L.c, 0);
+            KERNEL_CHECK(h);
+            CUDA_TRY(cudaMemcpyAsync(L.host, L.c, sizeof(double), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
-            last_res = h->gcw_res_host[it - 1];
-            if (!(last_res == last_res)) {
-                desc_set_error("GCW: non-finite residual at iteration %d (non-finite S_vec or RijMat?)", it);
+            explicit_res = L.host[0];
+            if (explicit_res <= accept) {
+                converged = true;
+                for (int i = 0; i < 3; i++) h->gcw_theta[i] = i < d ? ev[i] : 0.0;
+                CUDA_TRY(cudaMemcpyAsync(h->X[1], X, n9 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+                break;
+            }
+            trust_estimate = false;
+            if (exhausted) {
+                desc_set_error("GCW: Krylov space exhausted but residual is %.3e", explicit_res);
                 return DESC_B200_ERR_NOCONV;
             }
-            // converged, or stagnated at the rounding floor
-            if (last_res <= tol) converged = true;
-            if (it >= 3 * poll && last_res <= 1e-11 && last_res >= 0.5 * h->gcw_res_host[it - 1 - poll]) converged = true;
         }
+        if (!must_restart) continue;
+        // ---- thick restart: basis = [kr Ritz blocks, pending block]; H = diag(theta) on the kept part
+        const int pending_old = nblk - 1;   // valid only when no breakdown happened
+        for (int o = 0; o < kr; o++)
+            CUDA_TRY(cudaMemcpyAsync(L.blk(o), L.blk(scratch + o), n9 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        if (!breakdown) {
+            if (pending_old != kr)
+                CUDA_TRY(cudaMemcpyAsync(L.blk(kr), L.blk(pending_old), n9 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        } else {
+            DESC_TRY(L.random_block(kr, kr, salt++));
+        }
+        std::fill(Hm.begin(), Hm.end(), 0.0);
+        for (int i = 0; i < 3 * kr; i++) Hm[i + (size_t)i * ld] = ev[i];
+        nproc = kr;
+        nblk = kr + 1;
+        restarts++;
     }
-    h->tm.gcw_iters = it;
-    h->gcw_last_res = last_res;
-    if (!converged && !(last_res <= 1e-9)) {
-        desc_set_error("GCW subspace iteration did not converge: residual %.3e after %d iterations", last_res, it);
+    h->tm.gcw_iters = total_spmv;
+    h->gcw_last_res = explicit_res;
+    if (!converged) {
+        desc_set_error("GCW block Lanczos did not converge: estimate %.3e, explicit residual %.3e after %d SpMVs (%d restarts)",
+                       est, explicit_res, total_spmv, restarts);
         return DESC_B200_ERR_NOCONV;
     }
-    // Rayleigh-Ritz in the converged subspace, back-transform, normalise, sign, project
-    if (spmv_grid > 0) {
-        k_gcw_spmv<<<spmv_grid, 256, 0, st>>>(h->rowstart, h->adj_nbr, h->adj_eid, h->Rij, h->gcw_coef, X, Y, n0, n1);
-        KERNEL_CHECK(h);
+    // back-transform V = D^-1/2 X, normalise columns, sign rule, project every node block to SO(3)
+    {
+        const double ident[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        for (int x = 0; x < 9; x++) L.host[x] = ident[x];
+        CUDA_TRY(cudaMemcpyAsync(h->gcw_small + SM_Z, L.host, 9 * sizeof(double), cudaMemcpyHostToDevice, st));
     }
-    DESC_TRY(desc_allgather_ranges(h, Y, sizeof(double), nb9));
-    k_gcw_reduce<<<GCW_RED_BLOCKS, GCW_RED_TB, 0, st>>>(X, Y, n, h->gcw_red);
+    double* X = h->X[1];
+    double* Vout = L.blk(0);
+    k_gcw_ritz_apply<<<GCW_RED_BLOCKS, GCW_RED_TB, 0, st>>>(X, h->isd, n, h->gcw_small, Vout, h->gcw_red);
     KERNEL_CHECK(h);
-    k_gcw_small_ritz<<<1, 1, 0, st>>>(h->gcw_red, GCW_RED_BLOCKS, h->gcw_small);
+    k_gcw_small_final<<<1, 1, 0, st>>>(h->gcw_red, GCW_RED_BLOCKS, Vout, h->gcw_small);
     KERNEL_CHECK(h);
-    k_gcw_ritz_apply<<<GCW_RED_BLOCKS, GCW_RED_TB, 0, st>>>(X, h->isd, n, h->gcw_small, Y, h->gcw_red);
+    k_gcw_project<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(Vout, h->gcw_small, n, h->R_est);
     KERNEL_CHECK(h);
-    k_gcw_small_final<<<1, 1, 0, st>>>(h->gcw_red, GCW_RED_BLOCKS, Y, h->gcw_small);
-    KERNEL_CHECK(h);
-    k_gcw_project<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(Y, h->gcw_small, n, h->R_est);
-    KERNEL_CHECK(h);
-    double flag = 0.0;
-    CUDA_TRY(cudaMemcpyAsync(&flag, h->gcw_small + SM_FLAG, sizeof(double), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(h->gcw_theta, h->gcw_small + SM_THETA, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    if (flag != 0.0) {
-        desc_set_error("GCW: Cholesky-QR breakdown (rank-deficient iterate)");
-        return DESC_B200_ERR_NOCONV;
-    }
     return DESC_B200_OK;
 }
