@@ -1,0 +1,104 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header
+declares, struct layouts match, the MEX gateway compiles, and without a GPU every compute entry
+point fails loudly (no CPU fallback).  No kernels are launched here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import desc_b200
+from desc_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "desc_b200.h")
+
+
+def test_library_exports_every_header_symbol():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(desc_b200_[a-z0-9_]+)\s*\(", text)))
+    assert len(declared) >= 18
+    assert sorted(declared) == sorted(_lib.SYMBOLS), "header and _lib.SYMBOLS disagree"
+    lib = _lib.load()
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert lib.desc_b200_version() == 100
+
+
+def test_struct_layouts_match_header(tmp_path):
+    """sizes/offsets of the ctypes mirrors equal what a C compiler lays out from the header"""
+    src = tmp_path / "sz.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "desc_b200.h"\n'
+        'int main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(desc_b200_opts), sizeof(desc_b200_step_rule),'
+        ' sizeof(desc_b200_timings), offsetof(desc_b200_step_rule,t), offsetof(desc_b200_opts,nccl_id),'
+        ' offsetof(desc_b200_timings,pgd_launches), offsetof(desc_b200_opts,stream));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    mine = [C.sizeof(_lib.Opts), C.sizeof(_lib.StepRule), C.sizeof(_lib.Timings), _lib.StepRule.t.offset,
+            _lib.Opts.nccl_id.offset, _lib.Timings.pgd_launches.offset, _lib.Opts.stream.offset]
+    assert got == mine
+
+
+def test_mex_gateway_compiles_against_stub_header():
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "mex", "stub"),
+                        "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "mex", "desc_b200_mex.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for shim in ("DESC.m", "DESC_PGD.m", "DESC_init.m", "GCW.m", "desc_b200_rule.m", "desc_b200_run.m"):
+        assert os.path.exists(os.path.join(ROOT, "matlab", shim))
+
+
+def test_header_is_plain_c():
+    r = subprocess.run(["gcc", "-x", "c", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", HEADER],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_product_package_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "desc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".c")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_host_side_argument_checks():
+    with pytest.raises(ValueError):
+        desc_b200.Solver(np.zeros((3, 3)), np.zeros((3, 3, 3)))
+    with pytest.raises(ValueError):
+        desc_b200.Solver(np.array([[1.0, 2.0]]), np.zeros((3, 3, 2)))
+    with pytest.raises(ValueError):
+        desc_b200.DESC_PGD(np.array([[1.0, 2.0]]), np.zeros((3, 3, 1)), dict(iters=1, Gradient=None))
+    with pytest.raises(NotImplementedError):
+        desc_b200.DESC_PGD(np.array([[1.0, 2.0]]), np.zeros((3, 3, 1)),
+                           dict(iters=1, Gradient=desc_b200.ConstantStepSize(1.0), make_plots=True))
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    lib = _lib.load()
+    if lib.desc_b200_device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    Ind = np.array([[1.0, 2.0], [1.0, 3.0], [2.0, 3.0]])
+    R = np.stack([np.eye(3)] * 3, axis=2)
+    with pytest.raises(desc_b200.DescError) as e:
+        desc_b200.DESC_init(Ind, R, dict(iters=2, Gradient=desc_b200.ConstantStepSize(0.1)))
+    assert e.value.code == _lib.ERR_CUDA
+    with pytest.raises(desc_b200.DescError):
+        desc_b200.GCW(Ind, None, R, np.ones(3))
+
+
+def test_sampler_key_known_answer():
+    """desc_key of csrc/internal.cuh and oracle.sampler_keys are the same arithmetic; pin one value
+    computed by hand-expanding the mix so both sides can be checked against a constant."""
+    from oracle.desc_oracle import sampler_keys
+    z = (0 + 0x9E3779B97F4A7C15 * 1) & (2 ** 64 - 1)
+    z ^= (0xD1B54A32D192ED03 * 1) & (2 ** 64 - 1)
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2 ** 64 - 1)
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
+    z ^= z >> 31
+    assert int(sampler_keys(0, 0, 0)) == z
