@@ -70,11 +70,13 @@ void desc_b200_destroy(desc_b200_handle* h) {
                     h->codeg, h->rowptr, h->apex, h->pk_jk, h->pk_ki, h->S0, h->w[0], h->w[1],
                     h->S[0], h->S[1], h->acc[0], h->acc[1], h->adam_m, h->adam_v, h->d_hist, h->d_ctrl,
                     h->d_ctrl_f, h->omega, h->isd, h->X[0], h->X[1], h->gcw_coef, h->gcw_red,
-                    h->gcw_small, h->gcw_res, h->R_est, h->d_err, h->d_Sin};
+                    h->gcw_small, h->gcw_res, h->R_est, h->d_err, h->d_Sin, h->rk_i, h->rk_j, h->estart,
+                    h->pgd_partial};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
     if (h->gcw_res_host) cudaFreeHost(h->gcw_res_host);
+    for (cudaEvent_t e : h->iter_events) cudaEventDestroy(e);
     cudaEvent_t evs[] = {h->ev0, h->ev1, h->ev2, h->ev3};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);

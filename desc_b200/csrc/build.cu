@@ -12,6 +12,8 @@
 //     IKJ_appears / JKI_appears flag (DESC.m:113,124).
 #include "internal.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <cmath>
 
@@ -118,6 +120,21 @@ __global__ void k_fill_adj(const int* __restrict__ ei, const int* __restrict__ e
     adj_eid[pj] = (int)e;
 }
 
+// estart[v] = first edge whose smaller endpoint is >= v (edges sorted by (i,j)); estart[n] = m
+__global__ void k_estart(const int* __restrict__ ei, int64_t m, int n, int* __restrict__ estart) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > n) return;
+    int64_t lo = 0, hi = m;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (ei[mid] < v)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    estart[v] = (int)lo;
+}
+
 int desc_graph_setup(desc_b200_handle* h, const double* d_Ind) {
     const int64_t m = h->m;
     cudaStream_t st = h->stream;
@@ -178,6 +195,23 @@ int desc_graph_setup(desc_b200_handle* h, const double* d_Ind) {
     k_fill_adj<<<gb, TB, 0, st>>>(h->ei, h->ej, m, h->bm, h->bmprefix, h->nwords, h->rowstart,
                                   h->adj_nbr, h->adj_eid);
     KERNEL_CHECK(h);
+    CUDA_TRY(cudaMalloc(&h->estart, (size_t)(n + 1) * sizeof(int)));
+    k_estart<<<(n + 1 + TB - 1) / TB, TB, 0, st>>>(h->ei, m, n, h->estart);
+    KERNEL_CHECK(h);
+    h->h_estart.resize(n + 1);
+    {
+        std::vector<int> rs(n + 1);
+        CUDA_TRY(cudaMemcpyAsync(rs.data(), h->rowstart, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h->h_estart.data(), h->estart, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        h->maxdeg = 0;
+        for (int v = 0; v < n; v++) h->maxdeg = std::max(h->maxdeg, rs[v + 1] - rs[v]);
+    }
+    h->blocked_ok = h->maxdeg <= DESC_BLOCKED_MAXDEG;
+    {
+        const char* force = getenv("DESC_B200_PGD_PATH");   // "generic" forces the atomic edge-range kernel (tests)
+        if (force && strcmp(force, "generic") == 0) h->blocked_ok = false;
+    }
     int iso = 0;
     CUDA_TRY(cudaMemcpyAsync(&iso, h->d_err + 2, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -345,6 +379,7 @@ struct FillArgs {
     const int64_t* rowptr;
     int* apex;              // global slot index
     uint32_t *pk_jk, *pk_ki;  // local slot index (slot - slot_base), may be null (apex only)
+    uint16_t *rk_i, *rk_j;    // ranks of the apex in rows i / j (null: not wanted)
     int64_t e0, e1;         // edges to process
     int64_t l0, l1;         // local edge range for pk_* output
     int64_t slot_base;
@@ -422,10 +457,16 @@ __global__ void k_fill_slots(FillArgs a) {
                 int k = ck[q];
                 a.apex[r0 + p] = k;
                 if (local) {
-                    int eik = a.adj_eid[a.rowstart[i] + desc_rank(a.bm, a.bmprefix, a.nwords, i, k)];
-                    int ejk = a.adj_eid[a.rowstart[j] + desc_rank(a.bm, a.bmprefix, a.nwords, j, k)];
+                    const int ri_k = desc_rank(a.bm, a.bmprefix, a.nwords, i, k);
+                    const int rj_k = desc_rank(a.bm, a.bmprefix, a.nwords, j, k);
+                    int eik = a.adj_eid[a.rowstart[i] + ri_k];
+                    int ejk = a.adj_eid[a.rowstart[j] + rj_k];
                     a.pk_ki[r0 - a.slot_base + p] = (uint32_t)eik | (i < k ? PK_SEL : 0u);
                     a.pk_jk[r0 - a.slot_base + p] = (uint32_t)ejk | (j < k ? PK_SEL : 0u);
+                    if (a.rk_i) {
+                        a.rk_i[r0 - a.slot_base + p] = (uint16_t)ri_k;
+                        a.rk_j[r0 - a.slot_base + p] = (uint16_t)rj_k;
+                    }
                 }
             }
             outpos += __popc(bal);
@@ -454,10 +495,16 @@ __global__ void k_fill_explicit(FillArgs a, int* __restrict__ err) {
                 atomicOr(err, ERRB_APEX);
                 continue;
             }
-            int eik = a.adj_eid[a.rowstart[i] + desc_rank(a.bm, a.bmprefix, a.nwords, i, k)];
-            int ejk = a.adj_eid[a.rowstart[j] + desc_rank(a.bm, a.bmprefix, a.nwords, j, k)];
+            const int ri_k = desc_rank(a.bm, a.bmprefix, a.nwords, i, k);
+            const int rj_k = desc_rank(a.bm, a.bmprefix, a.nwords, j, k);
+            int eik = a.adj_eid[a.rowstart[i] + ri_k];
+            int ejk = a.adj_eid[a.rowstart[j] + rj_k];
             a.pk_ki[s - a.slot_base] = (uint32_t)eik | (i < k ? PK_SEL : 0u);
             a.pk_jk[s - a.slot_base] = (uint32_t)ejk | (j < k ? PK_SEL : 0u);
+            if (a.rk_i) {
+                a.rk_i[s - a.slot_base] = (uint16_t)ri_k;
+                a.rk_j[s - a.slot_base] = (uint16_t)rj_k;
+            }
         }
     }
 }
@@ -489,7 +536,8 @@ __device__ __forceinline__ bool apex_lsearch(const int* __restrict__ apex, int64
 template <bool SORTED>
 __global__ void k_recip_flags(const int* __restrict__ ei, const int* __restrict__ ej,
                               const int64_t* __restrict__ rowptr, const int* __restrict__ apex,
-                              uint32_t* __restrict__ pk_jk, uint32_t* __restrict__ pk_ki, int64_t l0,
+                              uint32_t* __restrict__ pk_jk, uint32_t* __restrict__ pk_ki,
+                              uint16_t* __restrict__ rk_i, uint16_t* __restrict__ rk_j, int64_t l0,
                               int64_t l1, int64_t slot_base) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -506,6 +554,10 @@ __global__ void k_recip_flags(const int* __restrict__ ei, const int* __restrict_
                              : apex_lsearch(apex, rowptr[ejk], rowptr[ejk + 1], i);
             pk_ki[s - slot_base] = (pki & ~PK_APP) | (fa ? PK_APP : 0u);
             pk_jk[s - slot_base] = (pjk & ~PK_APP) | (fb ? PK_APP : 0u);
+            if (rk_i) {
+                rk_i[s - slot_base] = (uint16_t)((rk_i[s - slot_base] & RK_MASK) | (fa ? RK_APP : 0u));
+                rk_j[s - slot_base] = (uint16_t)((rk_j[s - slot_base] & RK_MASK) | (fb ? RK_APP : 0u));
+            }
         }
     }
 }
@@ -541,6 +593,9 @@ static void free_incidence(desc_b200_handle* h) {
     cudaFree(h->pk_jk);
     cudaFree(h->pk_ki);
     cudaFree(h->S0);
+    cudaFree(h->rk_i);
+    cudaFree(h->rk_j);
+    h->rk_i = h->rk_j = nullptr;
     for (int b = 0; b < 2; b++) {
         cudaFree(h->w[b]);
         h->w[b] = nullptr;
@@ -669,6 +724,22 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaFree(d_b));
     }
+    // align shard boundaries to vertex blocks (all edges with the same smaller endpoint stay together)
+    {
+        std::vector<int> v_of(h->world + 1, 0);
+        v_of[h->world] = n;
+        for (int r = 1; r < h->world; r++) {
+            if (h->shard_edges[r] >= m) {
+                v_of[r] = n;
+                h->shard_edges[r] = m;
+            } else {
+                CUDA_TRY(cudaMemcpy(&v_of[r], h->ei + h->shard_edges[r], sizeof(int), cudaMemcpyDeviceToHost));
+                h->shard_edges[r] = h->h_estart[v_of[r]];
+            }
+        }
+        h->v_begin = v_of[h->rank];
+        h->v_end = v_of[h->rank + 1];
+    }
     h->e_begin = h->shard_edges[h->rank];
     h->e_end = h->shard_edges[h->rank + 1];
     h->shard_slots.assign(h->world + 1, 0);
@@ -684,6 +755,10 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
     CUDA_TRY(cudaMalloc(&h->pk_jk, ns_alloc * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&h->pk_ki, ns_alloc * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&h->S0, ns_alloc * sizeof(double)));
+    if (h->blocked_ok) {
+        CUDA_TRY(cudaMalloc(&h->rk_i, ns_alloc * sizeof(uint16_t)));
+        CUDA_TRY(cudaMalloc(&h->rk_j, ns_alloc * sizeof(uint16_t)));
+    }
     CUDA_TRY(cudaMalloc(&h->w[0], ns_alloc * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->w[1], ns_alloc * sizeof(double)));
 
@@ -700,6 +775,8 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
     fa.apex = h->apex;
     fa.pk_jk = h->pk_jk;
     fa.pk_ki = h->pk_ki;
+    fa.rk_i = h->rk_i;
+    fa.rk_j = h->rk_j;
     fa.e0 = h->e_begin;
     fa.e1 = h->e_end;
     fa.l0 = h->e_begin;
@@ -738,11 +815,11 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
             DESC_TRY(desc_allgather_ranges(h, h->apex, sizeof(int), h->shard_slots));
         }
         if (h->apex_sorted)
-            k_recip_flags<true><<<warp_grid, 256, 0, st>>>(h->ei, h->ej, h->rowptr, h->apex, h->pk_jk,
-                                                          h->pk_ki, h->e_begin, h->e_end, h->slot_base);
+            k_recip_flags<true><<<warp_grid, 256, 0, st>>>(h->ei, h->ej, h->rowptr, h->apex, h->pk_jk, h->pk_ki,
+                                                          h->rk_i, h->rk_j, h->e_begin, h->e_end, h->slot_base);
         else
-            k_recip_flags<false><<<warp_grid, 256, 0, st>>>(h->ei, h->ej, h->rowptr, h->apex, h->pk_jk,
-                                                           h->pk_ki, h->e_begin, h->e_end, h->slot_base);
+            k_recip_flags<false><<<warp_grid, 256, 0, st>>>(h->ei, h->ej, h->rowptr, h->apex, h->pk_jk, h->pk_ki,
+                                                           h->rk_i, h->rk_j, h->e_begin, h->e_end, h->slot_base);
         KERNEL_CHECK(h);
     }
     h->built = true;

@@ -16,6 +16,9 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <map>
+#include <mutex>
+
 namespace {
 struct NcclApi {
     void* lib = nullptr;
@@ -86,6 +89,14 @@ extern "C" int desc_b200_nccl_unique_id(void* out128) {
     return DESC_B200_OK;
 }
 
+// Communicators are cached per (unique id, rank, world, device): a ncclUniqueId can initialise one
+// communicator only, while a caller typically solves many graphs (many handles) with the id it
+// broadcast once.  Handles borrow the cached communicator; desc_b200_comm_finalize() frees them.
+namespace {
+std::map<std::string, ncclComm_t> g_comms;
+std::mutex g_comms_mu;
+}  // namespace
+
 int desc_comm_init(desc_b200_handle* h, const void* nccl_id) {
     if (h->world <= 1) return DESC_B200_OK;
     if (!nccl_id) {
@@ -93,17 +104,31 @@ int desc_comm_init(desc_b200_handle* h, const void* nccl_id) {
         return DESC_B200_ERR_ARG;
     }
     DESC_TRY(nccl_load());
+    std::string key((const char*)nccl_id, 128);
+    key += "/" + std::to_string(h->rank) + "/" + std::to_string(h->world) + "/" + std::to_string(h->device);
+    std::lock_guard<std::mutex> lock(g_comms_mu);
+    auto it = g_comms.find(key);
+    if (it != g_comms.end()) {
+        h->comm = it->second;
+        return DESC_B200_OK;
+    }
     ncclUniqueId id;
     memcpy(&id, nccl_id, sizeof(id));
     ncclComm_t comm;
     NCCL_TRY(g_nccl.CommInitRank(&comm, h->world, id, h->rank));
+    g_comms[key] = comm;
     h->comm = comm;
     return DESC_B200_OK;
 }
 
-void desc_comm_destroy(desc_b200_handle* h) {
-    if (h->comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)h->comm);
-    h->comm = nullptr;
+void desc_comm_destroy(desc_b200_handle* h) { h->comm = nullptr; }
+
+extern "C" int desc_b200_comm_finalize(void) {
+    std::lock_guard<std::mutex> lock(g_comms_mu);
+    if (g_nccl.ok)
+        for (auto& kv : g_comms) g_nccl.CommDestroy(kv.second);
+    g_comms.clear();
+    return DESC_B200_OK;
 }
 
 int desc_allreduce_sum(desc_b200_handle* h, double* buf, int64_t count) {

@@ -44,6 +44,10 @@ void desc_set_error(const char* fmt, ...);
 #define PK_APP 0x80000000u
 #define PK_SEL 0x40000000u
 #define PK_MASK 0x3FFFFFFFu
+#define RK_APP 0x8000u
+#define RK_MASK 0x7FFFu
+// vertex-blocked PGD: shared memory per CTA = 8 B * (1 + warps) * padded max degree
+#define DESC_BLOCKED_MAXDEG 5000
 #define DESC_MAX_EDGES 0x3FFFFFFFll
 
 static constexpr int DESC_SMS = 148;  // B200
@@ -86,6 +90,17 @@ struct desc_b200_handle {
     std::vector<int64_t> shard_slots;  // world+1 slot boundaries (rowptr at shard_edges)
     uint32_t* pk_jk = nullptr;  // n_slots
     uint32_t* pk_ki = nullptr;  // n_slots
+    // vertex-blocked PGD path (pgd.cu): rank of the apex k in the adjacency row of i (resp. j),
+    // bit 15 = IKJ_appears (resp. JKI_appears).  Null when a degree exceeds the 15-bit/shared-memory limit.
+    uint16_t* rk_i = nullptr;   // n_slots
+    uint16_t* rk_j = nullptr;   // n_slots
+    int* estart = nullptr;      // n+1: first edge whose smaller endpoint is >= v (edges are (i,j)-sorted)
+    std::vector<int> h_estart;  // host copy
+    int maxdeg = 0;
+    int v_begin = 0, v_end = 0; // local vertex range (shards are aligned to vertex blocks)
+    bool blocked_ok = false;    // the vertex-blocked path is usable for this graph
+    double* pgd_partial = nullptr;  // 2 per CTA: objective / change partials (deterministic reduction)
+    std::vector<cudaEvent_t> iter_events;  // per-iteration kernel timing
     double* S0 = nullptr;       // n_slots
 
     // PGD state -------------------------------------------------------------------------

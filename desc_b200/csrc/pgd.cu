@@ -27,6 +27,25 @@
 // The simplex projection uses Michelot's active-set iteration: T <- (sum_{w>T} w - 1)/#{w>T}
 // until the active set stops shrinking.  It converges to the same threshold as the reference's
 // sort-and-scan (DESC.m:215-223) without sorting.
+//
+// Two implementations of the iteration share the arithmetic above:
+//
+//  * vertex-blocked (default): edges are (i,j)-sorted, so all edges with the same smaller endpoint
+//    i form one contiguous "vertex block".  One CTA per block keeps in shared memory (a) the S
+//    values of every edge incident to i, indexed by the rank of the other endpoint in i's adjacency
+//    row, and (b) per-warp private partner-sum accumulators with the same indexing.  For a slot
+//    (ij;k) the partner edge {i,k} is then a shared-memory lookup (rank stored per slot as 15 bits
+//    + the IKJ_appears flag); only S[{j,k}] is a global (L2-resident) gather.  The scatter "via i"
+//    is a plain read-modify-write in the warp-private table (apices within one edge are distinct,
+//    one edge per warp instruction => no conflicts), flushed once per CTA.  The scatter "via j"
+//    runs in a second, vertex-centric kernel (k_pgd_scatter<false>) that walks the slot lists of
+//    the edges whose LARGER endpoint is the vertex.  No atomics anywhere: every accumulator entry
+//    is owned by exactly one CTA per kernel, so the result is bit-reproducible, and the random
+//    8-byte traffic of the generic kernel (2 gathers + 2 atomics per slot) drops to one gather.
+//    Streamed bytes per slot: 30 (fused kernel) + 10 (scatter kernel) = the 40 B/slot of SURVEY 8d.
+//
+//  * generic (fallback when a vertex degree exceeds the shared-memory table, or
+//    DESC_B200_PGD_PATH=generic): edge-range kernel with FP64 atomicAdd scatter.
 #include "internal.cuh"
 
 #include <algorithm>
@@ -204,8 +223,10 @@ k_pgd_init(PgdArgs a) {
             a.w_next[s] = w0;
             sn += w0 * a.S0[s];
             const uint32_t pi = a.pk_ki[s], pj = a.pk_jk[s];
-            if (pi & PK_APP) atomicAdd(&a.acc_next[2 * (int64_t)(pi & PK_MASK) + ((pi & PK_SEL) ? 0 : 1)], w0);
-            if (pj & PK_APP) atomicAdd(&a.acc_next[2 * (int64_t)(pj & PK_MASK) + ((pj & PK_SEL) ? 0 : 1)], w0);
+            if (a.acc_next) {   // generic path only; the vertex-blocked path scatters in k_pgd_scatter
+                if (pi & PK_APP) atomicAdd(&a.acc_next[2 * (int64_t)(pi & PK_MASK) + ((pi & PK_SEL) ? 0 : 1)], w0);
+                if (pj & PK_APP) atomicAdd(&a.acc_next[2 * (int64_t)(pj & PK_MASK) + ((pj & PK_SEL) ? 0 : 1)], w0);
+            }
         }
         sn = group_sum<G>(sn);
         if (r == 0 && ns > 0) a.S_next[e] = sn;
@@ -215,7 +236,7 @@ k_pgd_init(PgdArgs a) {
 // objective of the final state when the loop ran out of iterations (no later kernel computes it)
 template <int G>
 __global__ void __launch_bounds__(256)
-k_pgd_obj(PgdArgs a) {
+k_pgd_obj(PgdArgs a, double* __restrict__ partial) {
     if (a.ctrl[0]) return;
     const int r = threadIdx.x & (G - 1);
     const int64_t grp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / G;
@@ -236,7 +257,12 @@ k_pgd_obj(PgdArgs a) {
     if (threadIdx.x == 0) {
         double o = 0.0;
         for (int x = 0; x < (int)(blockDim.x >> 5); x++) o += sh[x];
-        atomicAdd(&a.acc_next[2 * a.m], o);
+        if (partial) {   // fixed-order reduction by k_pgd_partials: bit-reproducible
+            partial[2 * blockIdx.x] = o;
+            partial[2 * blockIdx.x + 1] = 0.0;
+        } else {
+            atomicAdd(&a.acc_next[2 * a.m], o);
+        }
     }
 }
 
@@ -274,6 +300,336 @@ __global__ void k_pgd_finalize(const double* __restrict__ red, int t, int last, 
         }
         ctrlf[0] = obj;
     }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// vertex-blocked path
+// ------------------------------------------------------------------------------------------
+#define BLK_TB 128
+#define BLK_WARPS (BLK_TB / 32)
+
+struct BlkArgs {
+    PgdArgs p;
+    const uint16_t *rk_i, *rk_j;
+    const int *rowstart, *adj_nbr, *adj_eid, *estart;
+    const uint32_t* bm;
+    const int* bmprefix;
+    int nwords;
+    int v0, v1;        // local vertex range
+    int tstride;       // padded max degree (table stride)
+    double* partial;   // 2 per CTA of k_pgd_block
+};
+
+// shared tables: T_S[tstride] | T_acc[BLK_WARPS][tstride]
+__device__ __forceinline__ void blk_flush(const BlkArgs& a, int v, int deg, int rs, const double* T_acc,
+                                          double* __restrict__ acc_out) {
+    for (int r = threadIdx.x; r < deg; r += BLK_TB) {
+        double x = 0.0;
+#pragma unroll
+        for (int q = 0; q < BLK_WARPS; q++) x += T_acc[q * a.tstride + r];
+        const int e2 = a.adj_eid[rs + r];
+        const int k = a.adj_nbr[rs + r];
+        acc_out[2 * (int64_t)e2 + (v < k ? 0 : 1)] += x;   // owned by this CTA within this kernel
+    }
+}
+
+template <int G, int EPL, int RULE>
+__global__ void __launch_bounds__(BLK_TB)
+k_pgd_block(BlkArgs a) {
+    if (a.p.ctrl[0]) return;
+    extern __shared__ double sh[];
+    double* T_S = sh;
+    double* T_acc = sh + a.tstride;
+    const int v = a.v0 + blockIdx.x;
+    const int rs = a.rowstart[v];
+    const int deg = a.rowstart[v + 1] - rs;
+    for (int r = threadIdx.x; r < deg; r += BLK_TB) {
+        T_S[r] = a.p.S_cur[a.adj_eid[rs + r]];
+#pragma unroll
+        for (int q = 0; q < BLK_WARPS; q++) T_acc[q * a.tstride + r] = 0.0;
+    }
+    __syncthreads();
+    double* Tw = T_acc + (threadIdx.x >> 5) * a.tstride;
+    const int r = threadIdx.x & (G - 1);
+    const int gw = (threadIdx.x & 31) / G;       // group within the warp
+    constexpr int GPW = 32 / G;
+    const int e_lo = a.estart[v], e_hi = a.estart[v + 1];
+    double objp = 0.0, chgp = 0.0;
+    for (int eb = e_lo; eb < e_hi; eb += BLK_TB / G) {
+        const int e = eb + threadIdx.x / G;
+        const bool valid = e < e_hi;
+        int64_t s0 = 0;
+        int ns = 0;
+        double A = 0.0, B = 0.0;
+        if (valid) {
+            s0 = a.p.rowptr[e];
+            ns = (int)(a.p.rowptr[e + 1] - s0);
+            s0 -= a.p.slot_base;
+            if (ns > 0) {
+                A = a.p.acc_cur[2 * (int64_t)e];
+                B = a.p.acc_cur[2 * (int64_t)e + 1];
+            }
+        }
+        double w[EPL], d[EPL];
+        uint32_t pj[EPL];
+        uint32_t rk[EPL];
+#pragma unroll
+        for (int x = 0; x < EPL; x++) {
+            const int idx = r + x * G;
+            w[x] = 0.0;
+            d[x] = 0.0;
+            pj[x] = 0u;
+            rk[x] = 0u;
+            if (idx < ns) {
+                const int64_t s = s0 + idx;
+                w[x] = __ldcs(a.p.w_cur + s);
+                d[x] = __ldcs(a.p.S0 + s);
+                pj[x] = __ldcs(a.p.pk_jk + s);
+                rk[x] = __ldcs(a.rk_i + s);
+            }
+        }
+        double g[EPL];
+        double gsum = 0.0;
+#pragma unroll
+        for (int x = 0; x < EPL; x++) {
+            g[x] = 0.0;
+            if (r + x * G < ns) {
+                const double sg = a.p.S_cur[pj[x] & PK_MASK] + T_S[rk[x] & RK_MASK];
+                objp += w[x] * sg;
+                const double part = ((rk[x] & RK_APP) ? A : 0.0) + ((pj[x] & PK_APP) ? B : 0.0);
+                g[x] = sg + part * d[x];
+                gsum += g[x];
+            }
+        }
+        gsum = group_sum<G>(gsum);
+        const double gmean = ns > 0 ? gsum / (double)ns : 0.0;
+        double wsum = 0.0;
+#pragma unroll
+        for (int x = 0; x < EPL; x++) {
+            if (r + x * G < ns) {
+                const double gr = g[x] - gmean;
+                double step;
+                if (RULE == 0) {
+                    step = -a.p.lr * gr;
+                } else {
+                    const int64_t s = s0 + r + x * G;
+                    const double mt = a.p.beta1 * a.p.adam_m[s] + (1.0 - a.p.beta1) * gr;
+                    const double vt = a.p.beta2 * a.p.adam_v[s] + (1.0 - a.p.beta2) * (gr * gr);
+                    a.p.adam_m[s] = mt;
+                    a.p.adam_v[s] = vt;
+                    step = -a.p.lr * (mt / a.p.corr1) / (sqrt(vt / a.p.corr2) + 1e-8);
+                }
+                w[x] = w[x] + step;
+                wsum += w[x];
+            }
+        }
+        wsum = group_sum<G>(wsum);
+        int cnt = ns;
+        double T = ns > 0 ? (wsum - 1.0) / (double)ns : 0.0;
+        for (int mit = 0; mit < G * EPL + 2; mit++) {
+            double s2 = 0.0;
+            int c2 = 0;
+#pragma unroll
+            for (int x = 0; x < EPL; x++) {
+                if (r + x * G < ns && w[x] > T) {
+                    s2 += w[x];
+                    c2++;
+                }
+            }
+            s2 = group_sum<G>(s2);
+            c2 = group_sum_int<G>(c2);
+            const bool changed = (c2 != cnt) && (c2 > 0);
+            if (changed) {
+                T = (s2 - 1.0) / (double)c2;
+                cnt = c2;
+            }
+            if (!__any_sync(0xffffffffu, changed)) break;
+        }
+        double snew = 0.0;
+#pragma unroll
+        for (int x = 0; x < EPL; x++) {
+            if (r + x * G < ns) {
+                const double wo = fmax(w[x] - T, 0.0);
+                w[x] = wo;
+                snew += wo * d[x];
+                __stcs(a.p.w_next + s0 + r + x * G, wo);
+            }
+        }
+        snew = group_sum<G>(snew);
+        if (ns > 0 && r == 0) {
+            a.p.S_next[e] = snew;
+            chgp += fabs(snew - a.p.S_cur[e]);
+        }
+        // scatter "via i" into the warp-private table: one edge (group) at a time so that the
+        // ranks touched by one instruction are distinct
+#pragma unroll
+        for (int q = 0; q < GPW; q++) {
+            __syncwarp();
+            if (gw == q) {
+#pragma unroll
+                for (int x = 0; x < EPL; x++)
+                    if (r + x * G < ns && (rk[x] & RK_APP)) Tw[rk[x] & RK_MASK] += w[x];
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    blk_flush(a, v, deg, rs, T_acc, a.p.acc_next);
+    objp = group_sum<32>(objp);
+    chgp = group_sum<32>(chgp);
+    __shared__ double red[2][BLK_WARPS];
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = objp;
+        red[1][threadIdx.x >> 5] = chgp;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double o = 0.0, c = 0.0;
+#pragma unroll
+        for (int q = 0; q < BLK_WARPS; q++) {
+            o += red[0][q];
+            c += red[1][q];
+        }
+        a.partial[2 * blockIdx.x] = o;
+        a.partial[2 * blockIdx.x + 1] = c;
+    }
+}
+
+// Vertex-centric scatter of w (state being built) into acc_next.
+//   OUT = true : own edges (v,*) of the local range, ranks rk_i          (used for state 0 only)
+//   OUT = false: edges (u,v) with u < v, u in the local vertex range, ranks rk_j ("via j")
+// One warp handles one edge at a time (distinct ranks per instruction), four edges in flight.
+template <bool OUT>
+__global__ void __launch_bounds__(BLK_TB)
+k_pgd_scatter(BlkArgs a, const double* __restrict__ w) {
+    if (a.p.ctrl[0]) return;
+    extern __shared__ double sh[];
+    double* T_acc = sh;
+    const int v = blockIdx.x;
+    const int rs = a.rowstart[v];
+    const int deg = a.rowstart[v + 1] - rs;
+    int lo, hi;   // OUT: edge ids; IN: adjacency positions
+    if (OUT) {
+        if (v < a.v0 || v >= a.v1) return;
+        lo = a.estart[v];
+        hi = a.estart[v + 1];
+    } else {
+        const int ub = min(a.v1, v);   // neighbours u with v0 <= u < ub
+        if (ub <= a.v0) return;
+        lo = rs + (a.v0 > 0 ? desc_rank(a.bm, a.bmprefix, a.nwords, v, a.v0) : 0);
+        hi = rs + desc_rank(a.bm, a.bmprefix, a.nwords, v, ub);
+    }
+    if (hi <= lo) return;
+    for (int r = threadIdx.x; r < deg; r += BLK_TB) {
+#pragma unroll
+        for (int q = 0; q < BLK_WARPS; q++) T_acc[q * a.tstride + r] = 0.0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* Tw = T_acc + warp * a.tstride;
+    const uint16_t* __restrict__ RK = OUT ? a.rk_i : a.rk_j;
+    constexpr int U = 4;
+    for (int base = lo + warp * U; base < hi; base += BLK_WARPS * U) {
+        int64_t s0[U];
+        int ns[U];
+#pragma unroll
+        for (int q = 0; q < U; q++) {
+            ns[q] = 0;
+            s0[q] = 0;
+            if (base + q < hi) {
+                const int e = OUT ? base + q : a.adj_eid[base + q];
+                s0[q] = a.p.rowptr[e];
+                ns[q] = (int)(a.p.rowptr[e + 1] - s0[q]);
+                s0[q] -= a.p.slot_base;
+            }
+        }
+        double wv[U];
+        uint32_t rk[U];
+#pragma unroll
+        for (int q = 0; q < U; q++) {
+            wv[q] = 0.0;
+            rk[q] = 0u;
+            if (lane < ns[q]) {
+                wv[q] = w[s0[q] + lane];
+                rk[q] = __ldcs(RK + s0[q] + lane);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < U; q++) {
+            if (rk[q] & RK_APP) Tw[rk[q] & RK_MASK] += wv[q];
+            __syncwarp();
+            for (int t = lane + 32; t < ns[q]; t += 32) {   // slot lists longer than a warp; the ranks
+                const uint32_t rr = RK[s0[q] + t];           // of one edge are distinct: no ordering needed
+                if (rr & RK_APP) Tw[rr & RK_MASK] += w[s0[q] + t];
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    blk_flush(a, v, deg, rs, T_acc, a.p.acc_next);
+}
+
+// fixed-order reduction of the per-CTA partials into red[0] (objective) and red[1] (change)
+__global__ void k_pgd_partials(const double* __restrict__ partial, int nblocks, const int* __restrict__ ctrl,
+                               double* __restrict__ red) {
+    if (ctrl[0]) return;
+    __shared__ double sh[2][256];
+    double o = 0.0, c = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 256) {
+        o += partial[2 * b];
+        c += partial[2 * b + 1];
+    }
+    sh[0][threadIdx.x] = o;
+    sh[1][threadIdx.x] = c;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + off];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        red[0] += sh[0][0];
+        red[1] += sh[1][0];
+    }
+}
+
+template <int G, int EPL>
+static int launch_block(desc_b200_handle* h, const BlkArgs& a, int rule_kind, size_t smem) {
+    const int nv = a.v1 - a.v0;
+    if (nv <= 0) return DESC_B200_OK;
+    if (rule_kind == 0) {
+        CUDA_TRY(cudaFuncSetAttribute(k_pgd_block<G, EPL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_pgd_block<G, EPL, 0><<<nv, BLK_TB, smem, h->stream>>>(a);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(k_pgd_block<G, EPL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_pgd_block<G, EPL, 1><<<nv, BLK_TB, smem, h->stream>>>(a);
+    }
+    KERNEL_CHECK(h);
+    return DESC_B200_OK;
+}
+
+static int launch_block_any(desc_b200_handle* h, const BlkArgs& a, int rule_kind, size_t smem) {
+    const int ns = h->max_ns;
+    if (ns <= 32) return launch_block<8, 4>(h, a, rule_kind, smem);
+    if (ns <= 64) return launch_block<16, 4>(h, a, rule_kind, smem);
+    if (ns <= 128) return launch_block<32, 4>(h, a, rule_kind, smem);
+    if (ns <= 256) return launch_block<32, 8>(h, a, rule_kind, smem);
+    if (ns <= 512) return launch_block<32, 16>(h, a, rule_kind, smem);
+    if (ns <= 1024) return launch_block<32, 32>(h, a, rule_kind, smem);
+    desc_set_error("an edge has %d slots; the fused PGD kernel supports at most 1024 per edge "
+                   "(lower n_sample)", ns);
+    return DESC_B200_ERR_LIMIT;
+}
+
+template <bool OUT>
+static int launch_scatter(desc_b200_handle* h, const BlkArgs& a, const double* w, size_t smem) {
+    CUDA_TRY(cudaFuncSetAttribute(k_pgd_scatter<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_pgd_scatter<OUT><<<h->n, BLK_TB, smem, h->stream>>>(a, w);
+    KERNEL_CHECK(h);
+    return DESC_B200_OK;
 }
 
 template <int G, int EPL>
@@ -327,6 +683,7 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
     const int64_t m = h->m;
     const int64_t nacc = 2 * m + 2;
     const bool adam = rule->kind == 2 && rule->strategy == 0;
+    const bool blocked = h->blocked_ok && h->rk_i != nullptr;
     for (int b = 0; b < 2; b++) {
         if (!h->S[b]) CUDA_TRY(cudaMalloc(&h->S[b], m * sizeof(double)));
         if (!h->acc[b]) CUDA_TRY(cudaMalloc(&h->acc[b], nacc * sizeof(double)));
@@ -336,6 +693,8 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
         CUDA_TRY(cudaMalloc(&h->d_ctrl_f, 2 * sizeof(double)));
         CUDA_TRY(cudaMallocHost(&h->h_ctrl, 4 * sizeof(int)));
     }
+    if (blocked && !h->pgd_partial)
+        CUDA_TRY(cudaMalloc(&h->pgd_partial, (size_t)2 * (std::max(h->n, DESC_SMS * 8) + 1) * sizeof(double)));
     if (h->hist_cap < iters + 1) {
         cudaFree(h->d_hist);
         h->d_hist = nullptr;
@@ -377,18 +736,34 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
     a.beta2 = rule->beta_2;
     a.corr1 = a.corr2 = 1.0;
     a.lr = 0.0;
+    BlkArgs ba;
+    ba.rk_i = h->rk_i;
+    ba.rk_j = h->rk_j;
+    ba.rowstart = h->rowstart;
+    ba.adj_nbr = h->adj_nbr;
+    ba.adj_eid = h->adj_eid;
+    ba.estart = h->estart;
+    ba.bm = h->bm;
+    ba.bmprefix = h->bmprefix;
+    ba.nwords = h->nwords;
+    ba.v0 = h->v_begin;
+    ba.v1 = h->v_end;
+    ba.tstride = (h->maxdeg + 3) & ~3;
+    ba.partial = h->pgd_partial;
+    const size_t smem_blk = (size_t)(1 + BLK_WARPS) * ba.tstride * sizeof(double);
+    const size_t smem_sc = (size_t)BLK_WARPS * ba.tstride * sizeof(double);
     const int launches0 = h->launches;
     const int G = h->max_ns <= 32 ? 8 : (h->max_ns <= 64 ? 16 : 32);
     const int aux_grid = DESC_SMS * 8;
 
-    // ---- state 0
+    // ---- state 0: uniform weights, S = mean S0 (DESC.m:148-157), partner sums of state 0
     CUDA_TRY(cudaMemsetAsync(h->acc[0], 0, nacc * sizeof(double), st));
     a.w_cur = nullptr;
     a.w_next = h->w[0];
     a.S_cur = nullptr;
     a.S_next = h->S[0];
     a.acc_cur = nullptr;
-    a.acc_next = h->acc[0];
+    a.acc_next = blocked ? nullptr : h->acc[0];   // blocked path: no atomics in k_pgd_init
     if (h->n_slots > 0) {
         if (G == 8)
             k_pgd_init<8><<<aux_grid, 256, 0, st>>>(a);
@@ -397,14 +772,25 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
         else
             k_pgd_init<32><<<aux_grid, 256, 0, st>>>(a);
         KERNEL_CHECK(h);
+        if (blocked) {
+            a.acc_next = h->acc[0];
+            ba.p = a;
+            DESC_TRY(launch_scatter<true>(h, ba, h->w[0], smem_sc));
+            DESC_TRY(launch_scatter<false>(h, ba, h->w[0], smem_sc));
+        }
     }
     if (h->world > 1) {
         DESC_TRY(desc_allreduce_sum(h, h->acc[0], nacc));
         DESC_TRY(desc_allgather_ranges(h, h->S[0], sizeof(double), h->shard_edges));
     }
 
-    cudaEvent_t evk0 = h->ev2, evk1 = h->ev3;
-    CUDA_TRY(cudaEventRecord(evk0, st));
+    // per-iteration kernel timing: events around the iteration kernels only
+    std::vector<cudaEvent_t>& evs = h->iter_events;
+    while ((int)evs.size() < 2 * std::min(iters, 512)) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        evs.push_back(e);
+    }
     int t_done = 0;
     bool stopped = false;
     const int check_every = 8;
@@ -423,7 +809,18 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
             a.corr1 = 1.0 - std::pow(rule->beta_1, (double)tcall);
             a.corr2 = 1.0 - std::pow(rule->beta_2, (double)tcall);
         }
-        DESC_TRY(launch_iter_any(h, a, adam ? 1 : 0));
+        const bool timed = t <= 512;
+        if (timed) CUDA_TRY(cudaEventRecord(evs[2 * (t - 1)], st));
+        if (blocked) {
+            ba.p = a;
+            DESC_TRY(launch_block_any(h, ba, adam ? 1 : 0, smem_blk));
+            DESC_TRY(launch_scatter<false>(h, ba, h->w[nxt], smem_sc));
+            k_pgd_partials<<<1, 256, 0, st>>>(h->pgd_partial, h->v_end - h->v_begin, h->d_ctrl, h->acc[nxt] + 2 * m);
+            KERNEL_CHECK(h);
+        } else {
+            DESC_TRY(launch_iter_any(h, a, adam ? 1 : 0));
+        }
+        if (timed) CUDA_TRY(cudaEventRecord(evs[2 * (t - 1) + 1], st));
         if (h->world > 1) {
             DESC_TRY(desc_allreduce_sum(h, h->acc[nxt], nacc));
             DESC_TRY(desc_allgather_ranges(h, h->S[nxt], sizeof(double), h->shard_edges));
@@ -437,7 +834,6 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
             stopped = h->h_ctrl[0] != 0;
         }
     }
-    CUDA_TRY(cudaEventRecord(evk1, st));
     int final_iter = 0;
     if (stopped) {
         final_iter = h->h_ctrl[1];
@@ -449,13 +845,18 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
         a.S_cur = h->S[cur];
         a.acc_next = h->acc[nxt];
         if (h->n_slots > 0) {
+            double* part = blocked ? h->pgd_partial : nullptr;
             if (G == 8)
-                k_pgd_obj<8><<<aux_grid, 256, 0, st>>>(a);
+                k_pgd_obj<8><<<aux_grid, 256, 0, st>>>(a, part);
             else if (G == 16)
-                k_pgd_obj<16><<<aux_grid, 256, 0, st>>>(a);
+                k_pgd_obj<16><<<aux_grid, 256, 0, st>>>(a, part);
             else
-                k_pgd_obj<32><<<aux_grid, 256, 0, st>>>(a);
+                k_pgd_obj<32><<<aux_grid, 256, 0, st>>>(a, part);
             KERNEL_CHECK(h);
+            if (blocked) {
+                k_pgd_partials<<<1, 256, 0, st>>>(h->pgd_partial, aux_grid, h->d_ctrl, h->acc[nxt] + 2 * m);
+                KERNEL_CHECK(h);
+            }
         }
         if (h->world > 1) DESC_TRY(desc_allreduce_sum(h, h->acc[nxt] + 2 * m, 2));
         k_pgd_finalize<<<1, 1, 0, st>>>(h->acc[nxt] + 2 * m, iters, 1, m, 1e-5, 30, h->d_hist, h->d_ctrl, h->d_ctrl_f);
@@ -467,9 +868,17 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
     h->have_pgd = true;
     *iters_run = final_iter;
     rule->t += final_iter;
-    float ms = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&ms, evk0, evk1));
+    // mean duration of the iteration kernels over the iterations that did real work
+    double sum_ms = 0.0;
+    int cnt = 0;
+    for (int t = 1; t <= std::min(std::min(t_done, 512), std::max(final_iter, 1)); t++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, evs[2 * (t - 1)], evs[2 * (t - 1) + 1]) == cudaSuccess) {
+            sum_ms += ms;
+            cnt++;
+        }
+    }
     h->tm.pgd_launches = h->launches - launches0;
-    h->tm.pgd_iter_ms = t_done > 0 ? ms / t_done : 0.0;
+    h->tm.pgd_iter_ms = cnt > 0 ? sum_ms / cnt : 0.0;
     return DESC_B200_OK;
 }

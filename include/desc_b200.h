@@ -102,6 +102,9 @@ int desc_b200_version(void);
 int desc_b200_device_count(void);
 /* fills 128 bytes with a fresh ncclUniqueId (call on rank 0, broadcast, pass via opts) */
 int desc_b200_nccl_unique_id(void* out128);
+/* NCCL communicators are cached per (id, rank, world, device) and shared by all handles created
+   with the same id; this destroys them (call once at shutdown, after destroying the handles). */
+int desc_b200_comm_finalize(void);
 
 /* A1 (DESC.m:19-24): take the graph.  n may be 0 (= max(Ind(:)), as the reference does) or
    an explicit node count >= max(Ind(:)).  Validates the layout contract (1<=i<j<=n,
