@@ -652,7 +652,7 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
 
     int* d_ns = nullptr;
     CUDA_TRY(cudaMalloc(&d_ns, m * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&h->rowptr, (m + 1) * sizeof(int64_t)));
+    CUDA_TRY(cudaMalloc(&h->rowptr, (m + 4) * sizeof(int64_t)));   // +3: 16-byte widened bulk copies (pgd_stream.cuh)
     const bool explicit_lists = cyc_ptr != nullptr;
     if (explicit_lists) {
         if (!cyc_apex) {
@@ -750,7 +750,8 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
     h->slot_base = h->shard_slots[h->rank];
     h->n_slots = h->shard_slots[h->rank + 1] - h->slot_base;
 
-    const size_t ns_alloc = (size_t)std::max<int64_t>(h->n_slots, 1);
+    // + 16: the streamed PGD kernel widens its bulk copies to 16-byte boundaries (pgd_stream.cuh)
+    const size_t ns_alloc = (size_t)std::max<int64_t>(h->n_slots, 1) + 16;
     CUDA_TRY(cudaMalloc(&h->apex, (size_t)std::max<int64_t>(h->m_cycle, 1) * sizeof(int)));
     CUDA_TRY(cudaMalloc(&h->pk_jk, ns_alloc * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&h->pk_ki, ns_alloc * sizeof(uint32_t)));

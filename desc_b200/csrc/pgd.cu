@@ -596,6 +596,48 @@ __global__ void k_pgd_partials(const double* __restrict__ partial, int nblocks, 
     }
 }
 
+#include "pgd_stream.cuh"
+
+template <int G, int EPL>
+static int launch_stream(desc_b200_handle* h, const BlkArgs& a, int rule_kind) {
+    const int nv = a.v1 - a.v0;
+    if (nv <= 0) return DESC_B200_OK;
+    constexpr int TE = ST_NCW * 32 / G;
+    StreamArgs sa;
+    sa.b = a;
+    sa.tsc = (TE * h->max_ns + 16 + 7) & ~7;
+    const size_t fixed = st_fixed_bytes(TE, a.tstride, h->max_ns), stage = st_stage_bytes(sa.tsc, TE);
+    // prefer two CTAs per SM (one CTA's table prologue / flush overlaps the other's streaming)
+    int nst = 0;
+    for (int c = ST_MAXSTAGES; c >= 2 && !nst; c--)
+        if (fixed + c * stage <= 112 * 1024) nst = c;
+    for (int c = ST_MAXSTAGES; c >= 2 && !nst; c--)
+        if (fixed + c * stage <= 226 * 1024) nst = c;
+    if (!nst) return DESC_B200_ERR_LIMIT;   // caller falls back to the blocked kernel
+    sa.nstages = nst;
+    sa.max_ns = h->max_ns;
+    const size_t smem = fixed + nst * stage;
+    if (rule_kind == 0) {
+        CUDA_TRY(cudaFuncSetAttribute(k_pgd_stream<G, EPL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_pgd_stream<G, EPL, 0><<<nv, ST_THREADS, smem, h->stream>>>(sa);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(k_pgd_stream<G, EPL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_pgd_stream<G, EPL, 1><<<nv, ST_THREADS, smem, h->stream>>>(sa);
+    }
+    KERNEL_CHECK(h);
+    return DESC_B200_OK;
+}
+
+// DESC_B200_ERR_LIMIT = this graph does not fit the streamed kernel (use the blocked one)
+static int launch_stream_any(desc_b200_handle* h, const BlkArgs& a, int rule_kind) {
+    const int ns = h->max_ns;
+    if (ns <= 32) return launch_stream<8, 4>(h, a, rule_kind);
+    if (ns <= 64) return launch_stream<16, 4>(h, a, rule_kind);
+    if (ns <= 128) return launch_stream<32, 4>(h, a, rule_kind);
+    if (ns <= 256) return launch_stream<32, 8>(h, a, rule_kind);
+    return DESC_B200_ERR_LIMIT;
+}
+
 template <int G, int EPL>
 static int launch_block(desc_b200_handle* h, const BlkArgs& a, int rule_kind, size_t smem) {
     const int nv = a.v1 - a.v0;
@@ -684,8 +726,14 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
     const int64_t nacc = 2 * m + 2;
     const bool adam = rule->kind == 2 && rule->strategy == 0;
     const bool blocked = h->blocked_ok && h->rk_i != nullptr;
+    // DESC_B200_PGD_PATH = generic | blocked | stream (default: stream when the graph fits)
+    bool stream = blocked;
+    {
+        const char* force = getenv("DESC_B200_PGD_PATH");
+        if (force && strcmp(force, "blocked") == 0) stream = false;
+    }
     for (int b = 0; b < 2; b++) {
-        if (!h->S[b]) CUDA_TRY(cudaMalloc(&h->S[b], m * sizeof(double)));
+        if (!h->S[b]) CUDA_TRY(cudaMalloc(&h->S[b], (m + 4) * sizeof(double)));   // +4: 16-byte widened bulk copies
         if (!h->acc[b]) CUDA_TRY(cudaMalloc(&h->acc[b], nacc * sizeof(double)));
     }
     if (!h->d_ctrl) {
@@ -813,7 +861,12 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
         if (timed) CUDA_TRY(cudaEventRecord(evs[2 * (t - 1)], st));
         if (blocked) {
             ba.p = a;
-            DESC_TRY(launch_block_any(h, ba, adam ? 1 : 0, smem_blk));
+            int rc = stream ? launch_stream_any(h, ba, adam ? 1 : 0) : DESC_B200_ERR_LIMIT;
+            if (rc == DESC_B200_ERR_LIMIT) {
+                stream = false;
+                rc = launch_block_any(h, ba, adam ? 1 : 0, smem_blk);
+            }
+            DESC_TRY(rc);
             DESC_TRY(launch_scatter<false>(h, ba, h->w[nxt], smem_sc));
             k_pgd_partials<<<1, 256, 0, st>>>(h->pgd_partial, h->v_end - h->v_begin, h->d_ctrl, h->acc[nxt] + 2 * m);
             KERNEL_CHECK(h);
