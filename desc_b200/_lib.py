@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdesc_b200.so")
+# DESC_B200_LIB: load another build of the library (kernel-tuning experiments)
+LIB_PATH = os.environ.get("DESC_B200_LIB") or os.path.join(_HERE, "libdesc_b200.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_STATE, ERR_LIMIT, ERR_NCCL, ERR_NOCONV = 0, -1, -2, -3, -4, -5, -6
 INPUTS_ON_DEVICE = 1

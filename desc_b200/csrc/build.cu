@@ -555,11 +555,23 @@ __global__ void k_recip_flags(const int* __restrict__ ei, const int* __restrict_
             pk_ki[s - slot_base] = (pki & ~PK_APP) | (fa ? PK_APP : 0u);
             pk_jk[s - slot_base] = (pjk & ~PK_APP) | (fb ? PK_APP : 0u);
             if (rk_i) {
-                rk_i[s - slot_base] = (uint16_t)((rk_i[s - slot_base] & RK_MASK) | (fa ? RK_APP : 0u));
+                rk_i[s - slot_base] = (uint16_t)((rk_i[s - slot_base] & RK_MASK) | (fa ? RK_APP : 0u) | (fb ? RK_APP2 : 0u));
                 rk_j[s - slot_base] = (uint16_t)((rk_j[s - slot_base] & RK_MASK) | (fb ? RK_APP : 0u));
             }
         }
     }
+}
+
+// header of every adjacency position: (first local slot, slot count) of its edge; (0,0) for edges of
+// other shards.  Lets the pass over larger endpoints find an in-edge's slot list with one load.
+__global__ void k_jhdr(const int* __restrict__ adj_eid, const int64_t* __restrict__ rowptr, int64_t n2m,
+                       int64_t e0, int64_t e1, int64_t slot_base, int2* __restrict__ jhdr) {
+    const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n2m) return;
+    const int64_t e = adj_eid[p];
+    int2 h = make_int2(0, 0);
+    if (e >= e0 && e < e1) h = make_int2((int)(rowptr[e] - slot_base), (int)(rowptr[e + 1] - rowptr[e]));
+    jhdr[p] = h;
 }
 
 // slot-balanced contiguous edge ranges: boundary r = first edge whose rowptr >= r*m_cycle/world
@@ -595,7 +607,11 @@ static void free_incidence(desc_b200_handle* h) {
     cudaFree(h->S0);
     cudaFree(h->rk_i);
     cudaFree(h->rk_j);
+    cudaFree(h->jhdr);
+    cudaFree(h->sjk);
     h->rk_i = h->rk_j = nullptr;
+    h->jhdr = nullptr;
+    h->sjk = nullptr;
     for (int b = 0; b < 2; b++) {
         cudaFree(h->w[b]);
         h->w[b] = nullptr;
@@ -756,9 +772,14 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
     CUDA_TRY(cudaMalloc(&h->pk_jk, ns_alloc * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&h->pk_ki, ns_alloc * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&h->S0, ns_alloc * sizeof(double)));
-    if (h->blocked_ok) {
+    if (h->blocked_ok && h->n_slots < (1ll << 31) - 64) {   // (jhdr holds 32-bit local slot offsets)
         CUDA_TRY(cudaMalloc(&h->rk_i, ns_alloc * sizeof(uint16_t)));
         CUDA_TRY(cudaMalloc(&h->rk_j, ns_alloc * sizeof(uint16_t)));
+        CUDA_TRY(cudaMalloc(&h->sjk, ns_alloc * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->jhdr, (size_t)(2 * m + 32) * sizeof(int2)));
+        k_jhdr<<<(unsigned)((2 * m + TB - 1) / TB), TB, 0, st>>>(h->adj_eid, h->rowptr, 2 * m, h->e_begin, h->e_end,
+                                                               h->slot_base, h->jhdr);
+        KERNEL_CHECK(h);
     }
     CUDA_TRY(cudaMalloc(&h->w[0], ns_alloc * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->w[1], ns_alloc * sizeof(double)));

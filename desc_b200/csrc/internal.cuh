@@ -44,10 +44,13 @@ void desc_set_error(const char* fmt, ...);
 #define PK_APP 0x80000000u
 #define PK_SEL 0x40000000u
 #define PK_MASK 0x3FFFFFFFu
+// rank words (vertex-blocked / streamed PGD): rank of the apex in the adjacency row of i (rk_i) or
+// j (rk_j) in 14 bits; bit 15 = IKJ_appears (rk_i) / JKI_appears (rk_j); bit 14 of rk_i = JKI_appears
 #define RK_APP 0x8000u
-#define RK_MASK 0x7FFFu
+#define RK_APP2 0x4000u
+#define RK_MASK 0x3FFFu
 // vertex-blocked PGD: shared memory per CTA = 8 B * (1 + warps) * padded max degree
-#define DESC_BLOCKED_MAXDEG 5000
+#define DESC_BLOCKED_MAXDEG 5000   // (< 2^14: the rank field)
 #define DESC_MAX_EDGES 0x3FFFFFFFll
 
 static constexpr int DESC_SMS = 148;  // B200
@@ -94,6 +97,8 @@ struct desc_b200_handle {
     // bit 15 = IKJ_appears (resp. JKI_appears).  Null when a degree exceeds the 15-bit/shared-memory limit.
     uint16_t* rk_i = nullptr;   // n_slots
     uint16_t* rk_j = nullptr;   // n_slots
+    int2* jhdr = nullptr;       // 2m: per adjacency position (v, u<v): local first slot and slot count of edge (u,v)
+    double* sjk = nullptr;      // n_slots: S[e_jk] of the current state, written by the pass over larger endpoints
     int* estart = nullptr;      // n+1: first edge whose smaller endpoint is >= v (edges are (i,j)-sorted)
     std::vector<int> h_estart;  // host copy
     int maxdeg = 0;

@@ -597,45 +597,95 @@ __global__ void k_pgd_partials(const double* __restrict__ partial, int nblocks, 
 }
 
 #include "pgd_stream.cuh"
+#include "pgd_passb.cuh"
 
-template <int G, int EPL>
-static int launch_stream(desc_b200_handle* h, const BlkArgs& a, int rule_kind) {
+template <int G, int EPL, int NCW, int NSW>
+static int launch_stream(desc_b200_handle* h, const BlkArgs& a, int rule_kind, int want_ctas, bool dry) {
     const int nv = a.v1 - a.v0;
     if (nv <= 0) return DESC_B200_OK;
-    constexpr int TE = ST_NCW * 32 / G;
+    constexpr int TE = NCW * 32 / G;
     StreamArgs sa;
     sa.b = a;
-    sa.tsc = (TE * h->max_ns + 16 + 7) & ~7;
-    const size_t fixed = st_fixed_bytes(TE, a.tstride, h->max_ns), stage = st_stage_bytes(sa.tsc, TE);
-    // prefer two CTAs per SM (one CTA's table prologue / flush overlaps the other's streaming)
-    int nst = 0;
-    for (int c = ST_MAXSTAGES; c >= 2 && !nst; c--)
-        if (fixed + c * stage <= 112 * 1024) nst = c;
-    for (int c = ST_MAXSTAGES; c >= 2 && !nst; c--)
-        if (fixed + c * stage <= 226 * 1024) nst = c;
-    if (!nst) return DESC_B200_ERR_LIMIT;   // caller falls back to the blocked kernel
-    sa.nstages = nst;
     sa.max_ns = h->max_ns;
+    sa.trace = nullptr;
+    sa.trace_cta = 0;
+    static long long* g_trace = nullptr;
+    if (const char* tr = getenv("DESC_B200_TRACE")) {
+        if (!g_trace) {
+            cudaMalloc(&g_trace, 64 * 8 * sizeof(long long));
+            cudaMemset(g_trace, 0, 64 * 8 * sizeof(long long));
+        }
+        sa.trace = g_trace;
+        sa.trace_cta = atoi(tr);
+        static int calls = 0;
+        if (++calls == 12) {   // dump the trace of the 11th launch
+            long long hbuf[64 * 8];
+            cudaStreamSynchronize(h->stream);
+            cudaMemcpy(hbuf, g_trace, sizeof(hbuf), cudaMemcpyDeviceToHost);
+            FILE* f = fopen("gpurun_out/trace.txt", "w");
+            if (f) {
+                for (int t = 0; t < 64; t++) {
+                    for (int k = 0; k < 8; k++) fprintf(f, "%lld ", hbuf[t * 8 + k]);
+                    fprintf(f, "\n");
+                }
+                fclose(f);
+            }
+        }
+    }
+    sa.tsc = (TE * h->max_ns + G * EPL + 16 + 7) & ~7;
+    const size_t fixed = st_fixed_bytes(TE, a.tstride, h->max_ns, NSW), stage = st_stage_bytes(sa.tsc, TE);
+    // several CTAs per SM: one CTA's table prologue / flush overlaps the others' streaming.
+    // 228 KB of shared memory per SM, 1 KB reserved per CTA.
+    int nst = 0;
+    for (int ctas = want_ctas; ctas >= 1 && !nst; ctas--) {
+        const size_t budget = (size_t)(228 * 1024) / ctas - 1024 - 256;
+        for (int c = ST_MAXSTAGES; c >= 2 && !nst; c--)
+            if (fixed + c * stage <= budget) nst = c;
+    }
+    if (!nst) return DESC_B200_ERR_LIMIT;   // caller falls back to the blocked kernel
+    if (dry) return DESC_B200_OK;
+    sa.nstages = nst;
+    sa.sjk = h->sjk;
     const size_t smem = fixed + nst * stage;
+    constexpr int NT = (NCW + NSW + 1) * 32;
     if (rule_kind == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(k_pgd_stream<G, EPL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_pgd_stream<G, EPL, 0><<<nv, ST_THREADS, smem, h->stream>>>(sa);
+        CUDA_TRY(cudaFuncSetAttribute(k_pgd_stream<G, EPL, NCW, NSW, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_pgd_stream<G, EPL, NCW, NSW, 0><<<nv, NT, smem, h->stream>>>(sa);
     } else {
-        CUDA_TRY(cudaFuncSetAttribute(k_pgd_stream<G, EPL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_pgd_stream<G, EPL, 1><<<nv, ST_THREADS, smem, h->stream>>>(sa);
+        CUDA_TRY(cudaFuncSetAttribute(k_pgd_stream<G, EPL, NCW, NSW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_pgd_stream<G, EPL, NCW, NSW, 1><<<nv, NT, smem, h->stream>>>(sa);
     }
     KERNEL_CHECK(h);
     return DESC_B200_OK;
 }
 
-// DESC_B200_ERR_LIMIT = this graph does not fit the streamed kernel (use the blocked one)
-static int launch_stream_any(desc_b200_handle* h, const BlkArgs& a, int rule_kind) {
+// slots-per-lane variants of one (compute warps, scatter warps) shape; lanes per edge follow max_ns
+template <int EPL, int NCW, int NSW>
+static int launch_stream_ns(desc_b200_handle* h, const BlkArgs& a, int rule_kind, int ctas, bool dry) {
     const int ns = h->max_ns;
-    if (ns <= 32) return launch_stream<8, 4>(h, a, rule_kind);
-    if (ns <= 64) return launch_stream<16, 4>(h, a, rule_kind);
-    if (ns <= 128) return launch_stream<32, 4>(h, a, rule_kind);
-    if (ns <= 256) return launch_stream<32, 8>(h, a, rule_kind);
+    if (ns <= 32) return launch_stream<32 / EPL, EPL, NCW, NSW>(h, a, rule_kind, ctas, dry);
+    if (ns <= 64) return launch_stream<64 / EPL, EPL, NCW, NSW>(h, a, rule_kind, ctas, dry);
+    if (ns <= 128) return launch_stream<128 / EPL, EPL, NCW, NSW>(h, a, rule_kind, ctas, dry);
+    if (EPL >= 8 && ns <= 256) return launch_stream<(EPL >= 8 ? 256 / EPL : 32), EPL, NCW, NSW>(h, a, rule_kind, ctas, dry);
     return DESC_B200_ERR_LIMIT;
+}
+
+// DESC_B200_ERR_LIMIT = this graph does not fit the streamed kernel (use the blocked one).
+// DESC_B200_ST="<slots per lane>,<compute warps>,<scatter warps>,<CTAs per SM>" picks another
+// compiled launch shape (experiments).
+static int launch_stream_any(desc_b200_handle* h, const BlkArgs& a, int rule_kind, bool dry = false) {
+    int epl = 4, ncw = 8, nsw = 2, ctas = 2;
+    if (const char* o = getenv("DESC_B200_ST")) sscanf(o, "%d,%d,%d,%d", &epl, &ncw, &nsw, &ctas);
+#define ST_CASE(E, C, S) \
+    if (epl == E && ncw == C && nsw == S) return launch_stream_ns<E, C, S>(h, a, rule_kind, ctas, dry);
+    ST_CASE(4, 8, 2)
+    ST_CASE(4, 8, 1)
+    ST_CASE(4, 4, 1)
+    ST_CASE(4, 4, 2)
+    ST_CASE(8, 4, 1)
+#undef ST_CASE
+    desc_set_error("DESC_B200_ST=%d,%d,%d,%d is not a compiled launch shape", epl, ncw, nsw, ctas);
+    return DESC_B200_ERR_ARG;
 }
 
 template <int G, int EPL>
@@ -670,6 +720,42 @@ template <bool OUT>
 static int launch_scatter(desc_b200_handle* h, const BlkArgs& a, const double* w, size_t smem) {
     CUDA_TRY(cudaFuncSetAttribute(k_pgd_scatter<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_pgd_scatter<OUT><<<h->n, BLK_TB, smem, h->stream>>>(a, w);
+    KERNEL_CHECK(h);
+    return DESC_B200_OK;
+}
+
+// pass over larger endpoints of the streamed path: sjk <- S_t[e_jk], partner sums "via j" of w_t
+// (DESC_B200_PASSB=tma selects the TMA-fed kernel instead of the register-prefetch one; measured on
+// B200 at cfg 4: 1.58 ms vs 1.12 ms - two small bulk copies per in-edge are issue-bound)
+static int launch_passb(desc_b200_handle* h, const BlkArgs& a, const double* w_t) {
+    const char* mode = getenv("DESC_B200_PASSB");
+    if (mode && strcmp(mode, "tma") == 0) {
+        PassbArgs pa;
+        pa.b = a;
+        pa.w = w_t;
+        pa.jhdr = h->jhdr;
+        pa.sjk = h->sjk;
+        pa.wmax = (h->max_ns + 1 + 1) & ~1;
+        pa.rmax = (h->max_ns + 7 + 7) & ~7;
+        const size_t fixed = pt_fixed_bytes(a.tstride), stage = pt_stage_bytes(pa.wmax, pa.rmax);
+        int nst = 0;
+        for (int ctas = 2; ctas >= 1 && !nst; ctas--) {
+            const size_t budget = (size_t)(228 * 1024) / ctas - 1024 - 256;
+            for (int c = PT_MAXSTAGES; c >= 2 && !nst; c--)
+                if (fixed + c * stage <= budget) nst = c;
+        }
+        if (nst) {
+            pa.nstages = nst;
+            const size_t smem = fixed + nst * stage;
+            CUDA_TRY(cudaFuncSetAttribute(k_pgd_passb_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_pgd_passb_tma<<<h->n, PT_TB, smem, h->stream>>>(pa);
+            KERNEL_CHECK(h);
+            return DESC_B200_OK;
+        }
+    }
+    const size_t smem = (size_t)(1 + PB_WARPS) * a.tstride * sizeof(double);
+    CUDA_TRY(cudaFuncSetAttribute(k_pgd_passb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_pgd_passb<true><<<h->n, PB_TB, smem, h->stream>>>(a, w_t, h->jhdr, h->sjk);
     KERNEL_CHECK(h);
     return DESC_B200_OK;
 }
@@ -796,11 +882,16 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
     ba.nwords = h->nwords;
     ba.v0 = h->v_begin;
     ba.v1 = h->v_end;
-    ba.tstride = (h->maxdeg + 3) & ~3;
+    ba.tstride = (h->maxdeg + 1 + 3) & ~3;   // >= maxdeg + 1: the last entry is a dummy slot for inactive lanes
     ba.partial = h->pgd_partial;
     const size_t smem_blk = (size_t)(1 + BLK_WARPS) * ba.tstride * sizeof(double);
     const size_t smem_sc = (size_t)BLK_WARPS * ba.tstride * sizeof(double);
     const int launches0 = h->launches;
+    if (stream) {   // does this graph fit the streamed kernel (and the table of the second pass)?
+        ba.p = a;
+        stream = h->sjk != nullptr && launch_stream_any(h, ba, adam ? 1 : 0, true) == DESC_B200_OK &&
+                 (size_t)(1 + PB_WARPS) * ba.tstride * sizeof(double) <= 226 * 1024;
+    }
     const int G = h->max_ns <= 32 ? 8 : (h->max_ns <= 64 ? 16 : 32);
     const int aux_grid = DESC_SMS * 8;
 
@@ -824,13 +915,12 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
             a.acc_next = h->acc[0];
             ba.p = a;
             DESC_TRY(launch_scatter<true>(h, ba, h->w[0], smem_sc));
-            DESC_TRY(launch_scatter<false>(h, ba, h->w[0], smem_sc));
+            if (!stream) DESC_TRY(launch_scatter<false>(h, ba, h->w[0], smem_sc));
         }
     }
-    if (h->world > 1) {
-        DESC_TRY(desc_allreduce_sum(h, h->acc[0], nacc));
-        DESC_TRY(desc_allgather_ranges(h, h->S[0], sizeof(double), h->shard_edges));
-    }
+    if (h->world > 1) DESC_TRY(desc_allgather_ranges(h, h->S[0], sizeof(double), h->shard_edges));
+    if (stream && h->n_slots > 0) DESC_TRY(launch_passb(h, ba, h->w[0]));   // needs every rank's S_0
+    if (h->world > 1) DESC_TRY(desc_allreduce_sum(h, h->acc[0], nacc));
 
     // per-iteration kernel timing: events around the iteration kernels only
     std::vector<cudaEvent_t>& evs = h->iter_events;
@@ -844,7 +934,12 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
     const int check_every = 8;
     for (int t = 1; t <= iters && !stopped; t++) {
         const int cur = (t - 1) & 1, nxt = t & 1;
-        CUDA_TRY(cudaMemsetAsync(h->acc[nxt], 0, nacc * sizeof(double), st));
+        // the streamed kernel stores every partner-sum entry of its vertex range (no zero-fill needed
+        // on one GPU); the all-reduce over ranks and the other kernels accumulate into zeros
+        if (stream && h->world == 1)
+            CUDA_TRY(cudaMemsetAsync(h->acc[nxt] + 2 * m, 0, 2 * sizeof(double), st));
+        else
+            CUDA_TRY(cudaMemsetAsync(h->acc[nxt], 0, nacc * sizeof(double), st));
         a.w_cur = h->w[cur];
         a.w_next = h->w[nxt];
         a.S_cur = h->S[cur];
@@ -859,14 +954,17 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
         }
         const bool timed = t <= 512;
         if (timed) CUDA_TRY(cudaEventRecord(evs[2 * (t - 1)], st));
-        if (blocked) {
+        if (stream) {
+            // pass 1 (smaller endpoints): update; pass 2 (larger endpoints) needs all of S_t
             ba.p = a;
-            int rc = stream ? launch_stream_any(h, ba, adam ? 1 : 0) : DESC_B200_ERR_LIMIT;
-            if (rc == DESC_B200_ERR_LIMIT) {
-                stream = false;
-                rc = launch_block_any(h, ba, adam ? 1 : 0, smem_blk);
-            }
-            DESC_TRY(rc);
+            DESC_TRY(launch_stream_any(h, ba, adam ? 1 : 0));
+            if (h->world > 1) DESC_TRY(desc_allgather_ranges(h, h->S[nxt], sizeof(double), h->shard_edges));
+            DESC_TRY(launch_passb(h, ba, h->w[nxt]));
+            k_pgd_partials<<<1, 256, 0, st>>>(h->pgd_partial, h->v_end - h->v_begin, h->d_ctrl, h->acc[nxt] + 2 * m);
+            KERNEL_CHECK(h);
+        } else if (blocked) {
+            ba.p = a;
+            DESC_TRY(launch_block_any(h, ba, adam ? 1 : 0, smem_blk));
             DESC_TRY(launch_scatter<false>(h, ba, h->w[nxt], smem_sc));
             k_pgd_partials<<<1, 256, 0, st>>>(h->pgd_partial, h->v_end - h->v_begin, h->d_ctrl, h->acc[nxt] + 2 * m);
             KERNEL_CHECK(h);
@@ -876,7 +974,7 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
         if (timed) CUDA_TRY(cudaEventRecord(evs[2 * (t - 1) + 1], st));
         if (h->world > 1) {
             DESC_TRY(desc_allreduce_sum(h, h->acc[nxt], nacc));
-            DESC_TRY(desc_allgather_ranges(h, h->S[nxt], sizeof(double), h->shard_edges));
+            if (!stream) DESC_TRY(desc_allgather_ranges(h, h->S[nxt], sizeof(double), h->shard_edges));
         }
         k_pgd_finalize<<<1, 1, 0, st>>>(h->acc[nxt] + 2 * m, t, 0, m, 1e-5, 30, h->d_hist, h->d_ctrl, h->d_ctrl_f);
         KERNEL_CHECK(h);
