@@ -20,7 +20,7 @@ ERROR_NAMES = {ERR_ARG: "DESC_B200_ERR_ARG", ERR_CUDA: "DESC_B200_ERR_CUDA", ERR
 
 # every symbol include/desc_b200.h declares (tests check the library exports all of them)
 SYMBOLS = [
-    "desc_b200_last_error", "desc_b200_version", "desc_b200_device_count", "desc_b200_nccl_unique_id", "desc_b200_comm_finalize",
+    "desc_b200_last_error", "desc_b200_version", "desc_b200_device_count", "desc_b200_nccl_unique_id", "desc_b200_comm_finalize", "desc_b200_trim",
     "desc_b200_create", "desc_b200_destroy", "desc_b200_build_incidence", "desc_b200_cycle_inconsistency",
     "desc_b200_pgd", "desc_b200_gcw", "desc_b200_solve", "desc_b200_get_info", "desc_b200_get_codeg",
     "desc_b200_get_incidence", "desc_b200_get_slots", "desc_b200_get_s0", "desc_b200_get_w",

@@ -10,6 +10,12 @@
 
 #include <string.h>
 
+// ---- pooled device memory (pool.cu): every cudaMalloc / cudaFree of the library goes through it
+cudaError_t desc_pool_malloc(void** p, size_t bytes);
+cudaError_t desc_pool_free(void* p);
+#define cudaMalloc(p, n) desc_pool_malloc((void**)(p), (n))
+#define cudaFree(p) desc_pool_free((void*)(p))
+
 // ---- error plumbing -----------------------------------------------------------------
 void desc_set_error(const char* fmt, ...);
 

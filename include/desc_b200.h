@@ -105,6 +105,10 @@ int desc_b200_nccl_unique_id(void* out128);
 /* NCCL communicators are cached per (id, rank, world, device) and shared by all handles created
    with the same id; this destroys them (call once at shutdown, after destroying the handles). */
 int desc_b200_comm_finalize(void);
+/* The library keeps freed device buffers in a per-device pool and reuses them in later solves
+   (cudaMalloc/cudaFree of GB-sized buffers cost more than some kernels); this returns the cached
+   buffers to the driver.  No reference counterpart (MATLAB manages its own heap). */
+int desc_b200_trim(void);
 
 /* A1 (DESC.m:19-24): take the graph.  n may be 0 (= max(Ind(:)), as the reference does) or
    an explicit node count >= max(Ind(:)).  Validates the layout contract (1<=i<j<=n,
