@@ -753,9 +753,18 @@ static int launch_passb(desc_b200_handle* h, const BlkArgs& a, const double* w_t
             return DESC_B200_OK;
         }
     }
-    const size_t smem = (size_t)(1 + PB_WARPS) * a.tstride * sizeof(double);
-    CUDA_TRY(cudaFuncSetAttribute(k_pgd_passb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_pgd_passb<true><<<h->n, PB_TB, smem, h->stream>>>(a, w_t, h->jhdr, h->sjk);
+    // warps per CTA by the mean number of local in-edges per vertex (batches of PB_U edges per warp)
+    const double per_cta = (double)(h->e_end - h->e_begin) / std::max(h->n, 1);
+    int nw = per_cta >= 256 ? 8 : (per_cta >= 96 ? 4 : 2);
+    if (const char* o = getenv("DESC_B200_PB_WARPS")) nw = atoi(o);
+    const size_t smem = (size_t)(2 + nw) * a.tstride * sizeof(double);   // T_S, nw private tables, header tile
+#define PB_LAUNCH(NW)                                                                                              \
+    {                                                                                                              \
+        CUDA_TRY(cudaFuncSetAttribute(k_pgd_passb<true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_pgd_passb<true, NW><<<h->n, NW * 32, smem, h->stream>>>(a, w_t, h->jhdr, h->sjk);                          \
+    }
+    if (nw >= 8) PB_LAUNCH(8) else if (nw >= 4) PB_LAUNCH(4) else PB_LAUNCH(2)
+#undef PB_LAUNCH
     KERNEL_CHECK(h);
     return DESC_B200_OK;
 }
@@ -890,7 +899,7 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
     if (stream) {   // does this graph fit the streamed kernel (and the table of the second pass)?
         ba.p = a;
         stream = h->sjk != nullptr && launch_stream_any(h, ba, adam ? 1 : 0, true) == DESC_B200_OK &&
-                 (size_t)(1 + PB_WARPS) * ba.tstride * sizeof(double) <= 226 * 1024;
+                 (size_t)(2 + 8) * ba.tstride * sizeof(double) <= 226 * 1024;
     }
     const int G = h->max_ns <= 32 ? 8 : (h->max_ns <= 64 ? 16 : 32);
     const int aux_grid = DESC_SMS * 8;
@@ -929,6 +938,10 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
         CUDA_TRY(cudaEventCreate(&e));
         evs.push_back(e);
     }
+    const bool phases = getenv("DESC_B200_PHASES") != nullptr && stream;
+    cudaEvent_t pev[3] = {nullptr, nullptr, nullptr};
+    if (phases)
+        for (auto& e : pev) cudaEventCreate(&e);
     int t_done = 0;
     bool stopped = false;
     const int check_every = 8;
@@ -958,7 +971,9 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
             // pass 1 (smaller endpoints): update; pass 2 (larger endpoints) needs all of S_t
             ba.p = a;
             DESC_TRY(launch_stream_any(h, ba, adam ? 1 : 0));
+            if (phases && t == 10) cudaEventRecord(pev[0], st);
             if (h->world > 1) DESC_TRY(desc_allgather_ranges(h, h->S[nxt], sizeof(double), h->shard_edges));
+            if (phases && t == 10) cudaEventRecord(pev[1], st);
             DESC_TRY(launch_passb(h, ba, h->w[nxt]));
             k_pgd_partials<<<1, 256, 0, st>>>(h->pgd_partial, h->v_end - h->v_begin, h->d_ctrl, h->acc[nxt] + 2 * m);
             KERNEL_CHECK(h);
@@ -978,6 +993,17 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
         }
         k_pgd_finalize<<<1, 1, 0, st>>>(h->acc[nxt] + 2 * m, t, 0, m, 1e-5, 30, h->d_hist, h->d_ctrl, h->d_ctrl_f);
         KERNEL_CHECK(h);
+        if (phases && t == 10 && timed) {   // DESC_B200_PHASES: where does iteration 10 spend its time?
+            cudaEventRecord(pev[2], st);
+            cudaEventSynchronize(pev[2]);
+            float a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+            cudaEventElapsedTime(&a1, evs[2 * (t - 1)], pev[0]);
+            cudaEventElapsedTime(&a2, pev[0], pev[1]);
+            cudaEventElapsedTime(&a3, pev[1], evs[2 * (t - 1) + 1]);
+            cudaEventElapsedTime(&a4, evs[2 * (t - 1) + 1], pev[2]);
+            fprintf(stderr, "[desc_b200 rank %d] iteration 10: pass1 %.3f ms | allgather S %.3f | pass2 %.3f | allreduce+finalize %.3f\n",
+                    h->rank, a1, a2, a3, a4);
+        }
         t_done = t;
         if (t % check_every == 0 || t == iters) {
             CUDA_TRY(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -11,21 +11,24 @@
 // the (w, rank) loads of the next two batches of edges and the headers of the third in flight in
 // registers while it works on the current batch.
 // No atomics: every partner-sum entry (edge, side v) is owned by vertex v's CTA.
-#ifndef PB_WARPS
-#define PB_WARPS 8
-#endif
-#define PB_TB (PB_WARPS * 32)
 #ifndef PB_U
 #define PB_U 4
+#endif
+#ifndef PB_PF
+#define PB_PF 6                         // L2 prefetch distance in batches
 #endif
 #ifndef PB_DEPTH
 #define PB_DEPTH 2                      // batches of (w, rank) loads in flight ahead of the current one
 #endif
 
-template <bool WRITE_SJK>
-__global__ void __launch_bounds__(PB_TB)
+// PB_WARPS warps (= private tables) per CTA: 8 when a vertex has hundreds of local in-edges, fewer
+// (smaller CTAs, more of them per SM) when sharding over GPUs leaves each CTA little work, so that
+// the O(degree) table prologue / flush of one CTA overlaps the others'.
+template <bool WRITE_SJK, int PB_WARPS>
+__global__ void __launch_bounds__(PB_WARPS * 32)
 k_pgd_passb(BlkArgs a, const double* __restrict__ w, const int2* __restrict__ jhdr, double* __restrict__ sjk) {
     if (a.p.ctrl[0]) return;
+    constexpr int PB_TB = PB_WARPS * 32;
     extern __shared__ double sh[];
     double* T_S = sh;
     double* T_acc = sh + a.tstride;
@@ -37,10 +40,32 @@ k_pgd_passb(BlkArgs a, const double* __restrict__ w, const int2* __restrict__ jh
     const int lo = rs + (a.v0 > 0 ? desc_rank(a.bm, a.bmprefix, a.nwords, v, a.v0) : 0);
     const int hi = rs + desc_rank(a.bm, a.bmprefix, a.nwords, v, ub);
     if (hi <= lo) return;
-    for (int r = threadIdx.x; r < deg; r += PB_TB) {
-        if (WRITE_SJK) T_S[r] = a.p.S_next[a.adj_eid[rs + r]];
+    int2* shdr = reinterpret_cast<int2*>(T_acc + (size_t)PB_WARPS * a.tstride);   // headers of the in-edges [lo, hi)
+    // table prologue, KU entries per thread at a time: all index loads, then all S gathers, in flight
+    // together (a plain loop serialises two dependent global latencies per trip)
+    constexpr int KU = 5;
+    for (int rb = threadIdx.x; rb < deg; rb += PB_TB * KU) {
+        int e2[KU];
+        double sv[KU];
+        int2 hv[KU];
 #pragma unroll
-        for (int q = 0; q < PB_WARPS; q++) T_acc[q * a.tstride + r] = 0.0;
+        for (int k = 0; k < KU; k++) {
+            const int r = rb + k * PB_TB;
+            e2[k] = r < deg ? a.adj_eid[rs + r] : -1;
+            hv[k] = lo + r < hi ? __ldg(jhdr + lo + r) : make_int2(0, 0);
+        }
+#pragma unroll
+        for (int k = 0; k < KU; k++) sv[k] = (WRITE_SJK && e2[k] >= 0) ? a.p.S_next[e2[k]] : 0.0;
+#pragma unroll
+        for (int k = 0; k < KU; k++) {
+            const int r = rb + k * PB_TB;
+            if (r < deg) {
+                T_S[r] = sv[k];
+                shdr[r] = hv[k];
+#pragma unroll
+                for (int q = 0; q < PB_WARPS; q++) T_acc[q * a.tstride + r] = 0.0;
+            }
+        }
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -48,107 +73,114 @@ k_pgd_passb(BlkArgs a, const double* __restrict__ w, const int2* __restrict__ jh
     const uint16_t* __restrict__ RK = a.rk_j;
     const uint32_t dummy = (uint32_t)a.tstride - 1u;
     constexpr int U = PB_U;
-    // Register pipeline, four batches deep.  A header is loaded by lanes < U and broadcast with
-    // shuffles only one iteration LATER (a shuffle right after the load would stall on it):
-    //   iteration b: issue header load of batch b+3 | broadcast header b+2, issue its (w, rank) loads |
-    //                (w, rank) of b+1 in flight | work on batch b
-    int2 h0[U], h1[U], h2[U], h3[U];
-    double w0[U], w1[U], w2[U], w3[U];
-    uint32_t r0[U], r1[U], r2[U], r3[U];
-    auto load_raw = [&](int base) {
-        int2 mine = make_int2(0, 0);
-        if (lane < U && base + lane < hi) mine = __ldg(jhdr + base + lane);
-        return mine;
+    // Register pipeline: three buffers of U edges; while one is worked on, the (w, rank) loads of the
+    // next two are in flight.  The loop is unrolled over the three buffers so that no register holding
+    // an in-flight load is ever copied (a rotation `cur = next` would wait for the loads).  Headers
+    // come from shared memory, so a buffer's loads can be issued as soon as it is free.
+    struct Buf {
+        int2 h[U];
+        double w[U];
+        uint32_t r[U];
     };
-    auto bcast = [&](const int2 mine, int2 (&h_)[U]) {
+    auto load = [&](Buf& B, int bb) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            h_[u].x = __shfl_sync(0xffffffffu, mine.x, u);
-            h_[u].y = __shfl_sync(0xffffffffu, mine.y, u);
+            B.h[u] = bb + u < hi ? shdr[bb + u - lo] : make_int2(0, 0);
+            B.w[u] = 0.0;
+            B.r[u] = 0u;
+            if (lane < B.h[u].y) {
+                B.w[u] = __ldcs(w + B.h[u].x + lane);
+                B.r[u] = __ldcs(RK + B.h[u].x + lane);
+            }
         }
     };
-    auto load_data = [&](const int2 (&h_)[U], double (&w_)[U], uint32_t (&r_)[U]) {
+    // L2 prefetch of the chunks PB_PF batches ahead (headers are in shared memory, so the addresses
+    // are known long before the loads are issued): lanes 4u..4u+3 touch the three 128-byte lines of
+    // edge u's weights and the line of its ranks.  Takes the DRAM latency off the register pipeline.
+    auto prefetch = [&](int bb) {
+        const int u = lane >> 2, part = lane & 3;
+        if (u < U && bb + u < hi) {
+            const int2 hh = shdr[bb + u - lo];
+            if (part * 16 < hh.y) {
+                const void* ptr = part < 3 ? (const void*)(w + hh.x + part * 16) : (const void*)(RK + hh.x);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+            }
+        }
+    };
+    auto work = [&](const Buf& B) {
+        // branch-free: inactive lanes (past the list end / flag off) use the dummy table entry
+        double ts[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) ts[u] = T_S[lane < B.h[u].y ? (B.r[u] & RK_MASK) : dummy];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            w_[u] = 0.0;
-            r_[u] = 0u;
-            if (lane < h_[u].y) {
-                w_[u] = __ldcs(w + h_[u].x + lane);
-                r_[u] = __ldcs(RK + h_[u].x + lane);
+            if (WRITE_SJK) {
+                if (lane < B.h[u].y) __stcs(sjk + B.h[u].x + lane, ts[u]);
+            }
+            const bool f = (B.r[u] & RK_APP) != 0u;
+            const uint32_t ia = f ? (B.r[u] & RK_MASK) : dummy;
+            const double t = TA[ia];
+            TA[ia] = t + (f ? B.w[u] : 0.0);
+            __syncwarp();
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (B.h[u].y > 32) {   // slot lists longer than a warp (ranks of one edge are distinct)
+                for (int i2 = lane + 32; i2 < B.h[u].y; i2 += 32) {
+                    const uint32_t rr = RK[B.h[u].x + i2];
+                    if (WRITE_SJK) sjk[B.h[u].x + i2] = T_S[rr & RK_MASK];
+                    if (rr & RK_APP) TA[rr & RK_MASK] += w[B.h[u].x + i2];
+                }
+                __syncwarp();
             }
         }
     };
     const int stride = PB_WARPS * U;
     int base = lo + warp * U;
-    {
-        const int2 a0 = load_raw(base), a1 = load_raw(base + stride), a2 = load_raw(base + 2 * stride);
-        bcast(a0, h0);
-        bcast(a1, h1);
-        if (PB_DEPTH == 3) bcast(a2, h2);
-    }
-    int2 raw = load_raw(base + PB_DEPTH * stride);
-    load_data(h0, w0, r0);
-    load_data(h1, w1, r1);
-    if (PB_DEPTH == 3) load_data(h2, w2, r2);
-    for (; base < hi; base += stride) {
-        const int2 raw_next = load_raw(base + (PB_DEPTH + 1) * stride);
-        if (PB_DEPTH == 3) {
-            bcast(raw, h3);
-            load_data(h3, w3, r3);
-        } else {
-            bcast(raw, h2);
-            load_data(h2, w2, r2);
-        }
-        raw = raw_next;
-        // branch-free: inactive lanes (past the list end / flag off) use the dummy table entry
-        double ts[U];
+    Buf X, Y, Z;
+    load(X, base);
+    load(Y, base + stride);
+    load(Z, base + 2 * stride);
 #pragma unroll
-        for (int u = 0; u < U; u++) ts[u] = T_S[lane < h0[u].y ? (r0[u] & RK_MASK) : dummy];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (WRITE_SJK) {
-                if (lane < h0[u].y) __stcs(sjk + h0[u].x + lane, ts[u]);
-            }
-            const bool f = (r0[u] & RK_APP) != 0u;
-            const uint32_t ia = f ? (r0[u] & RK_MASK) : dummy;
-            const double t = TA[ia];
-            TA[ia] = t + (f ? w0[u] : 0.0);
-            __syncwarp();
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (h0[u].y > 32) {   // slot lists longer than a warp (ranks of one edge are distinct)
-                for (int i2 = lane + 32; i2 < h0[u].y; i2 += 32) {
-                    const uint32_t rr = RK[h0[u].x + i2];
-                    if (WRITE_SJK) sjk[h0[u].x + i2] = T_S[rr & RK_MASK];
-                    if (rr & RK_APP) TA[rr & RK_MASK] += w[h0[u].x + i2];
-                }
-                __syncwarp();
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            h0[u] = h1[u];
-            h1[u] = h2[u];
-            w0[u] = w1[u];
-            w1[u] = w2[u];
-            r0[u] = r1[u];
-            r1[u] = r2[u];
-            if (PB_DEPTH == 3) {
-                h2[u] = h3[u];
-                w2[u] = w3[u];
-                r2[u] = r3[u];
-            }
-        }
+    for (int k = 3; k < 3 + PB_PF; k++) prefetch(base + k * stride);
+    while (base < hi) {
+        work(X);
+        load(X, base + 3 * stride);
+        prefetch(base + (3 + PB_PF) * stride);
+        if (base + stride >= hi) break;
+        work(Y);
+        load(Y, base + 4 * stride);
+        prefetch(base + (4 + PB_PF) * stride);
+        if (base + 2 * stride >= hi) break;
+        work(Z);
+        load(Z, base + 5 * stride);
+        prefetch(base + (5 + PB_PF) * stride);
+        base += 3 * stride;
     }
     __syncthreads();
-    for (int r = threadIdx.x; r < deg; r += PB_TB) {
-        double x = 0.0;
+    // flush (every entry (edge, side v) is owned by this CTA within this kernel), KU entries per
+    // thread at a time so that the index loads and the read-modify-writes overlap
+    for (int rb = threadIdx.x; rb < deg; rb += PB_TB * KU) {
+        int64_t pos[KU];
+        double old[KU];
 #pragma unroll
-        for (int q = 0; q < PB_WARPS; q++) x += T_acc[q * a.tstride + r];
-        const int e2 = a.adj_eid[rs + r];
-        const int k = a.adj_nbr[rs + r];
-        a.p.acc_next[2 * (int64_t)e2 + (v < k ? 0 : 1)] += x;   // owned by this CTA within this kernel
+        for (int k = 0; k < KU; k++) {
+            const int r = rb + k * PB_TB;
+            pos[k] = -1;
+            if (r < deg) pos[k] = 2 * (int64_t)a.adj_eid[rs + r] + (v < a.adj_nbr[rs + r] ? 0 : 1);
+        }
+#pragma unroll
+        for (int k = 0; k < KU; k++) old[k] = pos[k] >= 0 ? a.p.acc_next[pos[k]] : 0.0;
+#pragma unroll
+        for (int k = 0; k < KU; k++) {
+            const int r = rb + k * PB_TB;
+            if (r < deg) {
+                double x = 0.0;
+#pragma unroll
+                for (int q = 0; q < PB_WARPS; q++) x += T_acc[q * a.tstride + r];
+                a.p.acc_next[pos[k]] = old[k] + x;
+            }
+        }
     }
 }
 

@@ -28,6 +28,9 @@
 // covers the 16-byte aligned interior of [sA, sB); a ragged first / last element is stored directly.
 
 #define ST_MAXSTAGES 4
+#ifndef ST_TPW
+#define ST_TPW 1                       // private partner-sum tables per scatter warp (1 or 2)
+#endif
 
 __device__ __forceinline__ uint32_t st_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -100,7 +103,7 @@ __host__ __device__ __forceinline__ size_t st_stage_bytes(int tsc, int te) {
 __host__ __device__ __forceinline__ size_t st_rcp_bytes(int max_ns) { return ((size_t)(max_ns + 1) * 8 + 15) & ~(size_t)15; }
 __host__ __device__ __forceinline__ size_t st_fixed_bytes(int te, int tstride, int max_ns, int nsw) {
     return 128 + (size_t)ST_MAXSTAGES * te * sizeof(int2) + st_rcp_bytes(max_ns) +
-           (size_t)(1 + 2 * nsw) * tstride * sizeof(double);   // T_S + two private tables per scatter warp
+           (size_t)(1 + ST_TPW * nsw) * tstride * sizeof(double);   // T_S + the scatter warps' private tables
 }
 
 // G lanes per edge with EPL slots each, NCW compute warps, ST_NSW scatter warps (private tables),
@@ -121,7 +124,7 @@ k_pgd_stream(StreamArgs sa) {
     double* rcp = reinterpret_cast<double*>(smem_raw + 128 + (size_t)ST_MAXSTAGES * TE * sizeof(int2));
     double* T_S = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(rcp) + st_rcp_bytes(sa.max_ns));
     double* T_acc = T_S + a.tstride;
-    constexpr int NTAB = 2 * ST_NSW;
+    constexpr int NTAB = ST_TPW * ST_NSW;
     unsigned char* stage0 = reinterpret_cast<unsigned char*>(T_acc + (size_t)NTAB * a.tstride);
     const int tsc = sa.tsc;
     const size_t stage_bytes = st_stage_bytes(tsc, TE);
@@ -209,10 +212,24 @@ k_pgd_stream(StreamArgs sa) {
         // ------------------------------------------------------------------ tables (compute + scatter warps)
         constexpr int NT = (NCW + ST_NSW) * 32;
         for (int c = threadIdx.x; c <= sa.max_ns; c += NT) rcp[c] = c > 0 ? 1.0 / (double)c : 0.0;
-        for (int r = threadIdx.x; r < deg; r += NT) {
-            T_S[r] = a.p.S_cur[a.adj_eid[rs + r]];
+        // KU entries per thread at a time: index loads, then S gathers, all in flight together
+        constexpr int KU = 4;
+        for (int rb = threadIdx.x; rb < deg; rb += NT * KU) {
+            int e2[KU];
+            double sv[KU];
 #pragma unroll
-            for (int q = 0; q < NTAB; q++) T_acc[q * a.tstride + r] = 0.0;
+            for (int k = 0; k < KU; k++) e2[k] = rb + k * NT < deg ? a.adj_eid[rs + rb + k * NT] : -1;
+#pragma unroll
+            for (int k = 0; k < KU; k++) sv[k] = e2[k] >= 0 ? a.p.S_cur[e2[k]] : 0.0;
+#pragma unroll
+            for (int k = 0; k < KU; k++) {
+                const int r = rb + k * NT;
+                if (r < deg) {
+                    T_S[r] = sv[k];
+#pragma unroll
+                    for (int q = 0; q < NTAB; q++) T_acc[q * a.tstride + r] = 0.0;
+                }
+            }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
         if (warp < NCW) {
@@ -352,7 +369,7 @@ k_pgd_stream(StreamArgs sa) {
         } else {
             // -------------------------------------------------------------- scatter
             const int swi = warp - NCW;
-            double* Tw = T_acc + (size_t)(2 * swi) * a.tstride;
+            double* Tw = T_acc + (size_t)(ST_TPW * swi) * a.tstride;
             const uint32_t dummy = (uint32_t)a.tstride - 1u;
             const uint64_t pol = l2_evict_first_policy();
             int s = 0;
@@ -410,21 +427,30 @@ k_pgd_stream(StreamArgs sa) {
 #pragma unroll
                     for (int u = 0; u < U; u += 2) {
                         double* TA = Tw;
-                        double* TB = Tw + a.tstride;
+                        double* TB = Tw + (ST_TPW - 1) * a.tstride;
                         // branch-free: lanes without the flag update the dummy entry with 0
                         const bool fa = (rk[u] & RK_APP) != 0u, fb = (rk[u + 1] & RK_APP) != 0u;
                         const uint32_t ia = fa ? (rk[u] & RK_MASK) : dummy, ib = fb ? (rk[u + 1] & RK_MASK) : dummy;
-                        const double ta = TA[ia];
-                        const double tb = TB[ib];
-                        TA[ia] = ta + (fa ? wv[u] : 0.0);
-                        TB[ib] = tb + (fb ? wv[u + 1] : 0.0);
-                        __syncwarp();
+                        if (ST_TPW == 2) {   // two independent chains in flight
+                            const double ta = TA[ia];
+                            const double tb = TB[ib];
+                            TA[ia] = ta + (fa ? wv[u] : 0.0);
+                            TB[ib] = tb + (fb ? wv[u + 1] : 0.0);
+                            __syncwarp();
+                        } else {             // one table: edge after edge
+                            const double ta = TA[ia];
+                            TA[ia] = ta + (fa ? wv[u] : 0.0);
+                            __syncwarp();
+                            const double tb = TA[ib];
+                            TA[ib] = tb + (fb ? wv[u + 1] : 0.0);
+                            __syncwarp();
+                        }
                     }
                     // slot lists longer than a warp (ranks of one edge are distinct: no ordering needed inside)
 #pragma unroll
                     for (int u = 0; u < U; u++) {
                         if (nsu[u] > 32) {
-                            double* TT = Tw + (u & 1) * a.tstride;
+                            double* TT = Tw + (u & (ST_TPW - 1)) * a.tstride;
                             for (int i2 = lane + 32; i2 < nsu[u]; i2 += 32) {
                                 const uint32_t rr = srk[offu[u] + i2];
                                 if (rr & RK_APP) TT[rr & RK_MASK] += sw[offu[u] + i2];
@@ -459,13 +485,27 @@ k_pgd_stream(StreamArgs sa) {
     if (warp == 0) ST_TRACE(6, 1);
     // flush the private tables: every (edge, side) entry belongs to exactly one vertex block, and this
     // kernel is the first writer of acc_next in an iteration => plain stores (k_pgd_scatter adds later)
-    for (int r = threadIdx.x; r < deg; r += NTHREADS) {
-        double x = 0.0;
+    {
+        constexpr int KU = 4;
+        for (int rb = threadIdx.x; rb < deg; rb += NTHREADS * KU) {
+            int64_t pos[KU];
 #pragma unroll
-        for (int q = 0; q < NTAB; q++) x += T_acc[q * a.tstride + r];
-        const int e2 = a.adj_eid[rs + r];
-        const int k = a.adj_nbr[rs + r];
-        a.p.acc_next[2 * (int64_t)e2 + (v < k ? 0 : 1)] = x;
+            for (int k = 0; k < KU; k++) {
+                const int r = rb + k * NTHREADS;
+                pos[k] = -1;
+                if (r < deg) pos[k] = 2 * (int64_t)a.adj_eid[rs + r] + (v < a.adj_nbr[rs + r] ? 0 : 1);
+            }
+#pragma unroll
+            for (int k = 0; k < KU; k++) {
+                const int r = rb + k * NTHREADS;
+                if (r < deg) {
+                    double x = 0.0;
+#pragma unroll
+                    for (int q = 0; q < NTAB; q++) x += T_acc[q * a.tstride + r];
+                    a.p.acc_next[pos[k]] = x;
+                }
+            }
+        }
     }
     objp = group_sum<32>(objp);
     chgp = group_sum<32>(chgp);
