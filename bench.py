@@ -13,8 +13,11 @@ value  = 3-cycle evaluations per second over the whole step = m_cycle * iters_ru
          inputs (Ind, RijMat) already resident in HBM; N>1 shards the same problem ("strong").
 e2e    = the same through the reference-style call with HOST (pinned) buffers: H2D of Ind/RijMat
          and D2H of S_vec / R_est / history inside the timed region.
-roofline = the fused PGD-iteration kernel: algorithmic bytes (40*m_cycle + 12*m_pos + 8*m,
-         SURVEY 8d) / mean kernel duration (CUDA events on the launching stream) vs measured HBM peak.
+roofline = one PGD iteration = its two kernels (k_pgd_stream: update pass over smaller endpoints,
+         k_pgd_passb: table pass over larger endpoints): algorithmic bytes (40*m_cycle + 12*m_pos + 8*m,
+         SURVEY 8d) / mean duration of the pair (CUDA events on the launching stream around each
+         kernel) vs the measured HBM peak.  `traffic` = DRAM bytes of the pair from the committed ncu
+         capture (profiles/), valid for the default workload on one GPU.
 cpu_baseline = the oracle port timed on this box's host cores on a bounded sample.
 """
 import argparse
@@ -36,6 +39,7 @@ WORKLOADS = {
     "small": dict(n=2000, p=0.1, q=0.2, sigma=0.1, model="uniform", iters=100, lr=0.01,
                   name="Uniform_Topology n=2000 p=0.1 q=0.2 sigma=0.1 uniform, iters=100 ConstantStepSize(0.01)"),
 }
+NCU_TRAFFIC_CFG4 = 9005426000   # k_pgd_stream 5.654e9 + k_pgd_passb 3.351e9 (profiles/r01_v7_ncu_full_summary.txt)
 METRIC = "DESC 3-cycle evals/s (whole solve: incidence + d_ijk + PGD + GCW)"
 UNIT = "evals/s"
 
@@ -261,10 +265,17 @@ def run_gpu(args, wl):
         alg_bytes = 40.0 * local_slots + 12.0 * local_edges + 8.0 * info["m"]
         iter_ms = tm["pgd_iter_ms"]
         achieved = alg_bytes / (iter_ms * 1e-3) / 1e9 if iter_ms > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": "k_pgd_iter (fused PGD iteration)", "achieved": achieved, "peak": peak,
-                    "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        # DRAM bytes (read + write) of the two kernels of one iteration: `ncu --set full`, cfg 4, 1 GPU
+        # (profiles/r01_pgd_v7_*.txt); not meaningful for other workloads / shard sizes
+        traffic = NCU_TRAFFIC_CFG4 if (args.workload == "cfg4" and world == 1) else None
+        roofline = {"bound": "hbm",
+                    "kernel": "PGD iteration = k_pgd_stream (update, smaller endpoints) + k_pgd_passb (tables, larger endpoints)",
+                    "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic,
                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": iter_ms,
-                    "formula": "40*slots + 12*edges_with_cycles + 8*m (SURVEY 8d), per rank"}
+                    "kernels_ms": {"k_pgd_stream": tm.get("pgd_pass1_ms"), "k_pgd_passb": tm.get("pgd_pass2_ms")},
+                    "comm_ms_per_iteration": tm.get("pgd_comm_ms"),
+                    "formula": "40*slots + 12*edges_with_cycles + 8*m (SURVEY 8d), per rank, per iteration (both kernels)"}
         cpu = None
         if world == 1 and not args.no_cpu:
             v, dt, ci = cpu_sample(wl, args.cpu_n, args.cpu_iters)
@@ -280,7 +291,8 @@ def run_gpu(args, wl):
                            "parallelism": "edge-sharded x%d" % world},
                 "solve_s": ms_step * 1e-3,
                 "pgd_evals_per_s": evals / (tm["pgd_ms"] * 1e-3) if tm["pgd_ms"] > 0 else None,
-                "stages_ms": {k: tm[k] for k in ("graph_ms", "build_ms", "cycle_ms", "pgd_ms", "gcw_ms", "pgd_iter_ms")},
+                "stages_ms": {k: tm[k] for k in ("graph_ms", "build_ms", "cycle_ms", "pgd_ms", "gcw_ms", "pgd_iter_ms",
+                                                 "pgd_pass1_ms", "pgd_pass2_ms", "pgd_comm_ms")},
                 "gcw_iters": tm["gcw_iters"], "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(line), flush=True)

@@ -50,7 +50,8 @@ class Timings(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("graph_ms", C.c_double), ("build_ms", C.c_double), ("cycle_ms", C.c_double),
                 ("pgd_ms", C.c_double), ("gcw_ms", C.c_double), ("d2h_ms", C.c_double), ("pgd_iter_ms", C.c_double),
                 ("pgd_launches", C.c_int32), ("gcw_iters", C.c_int32), ("total_launches", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("pgd_pass1_ms", C.c_double), ("pgd_pass2_ms", C.c_double),
+                ("pgd_comm_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

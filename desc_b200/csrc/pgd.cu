@@ -931,15 +931,11 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
 
     // per-iteration kernel timing: events around the iteration kernels only
     std::vector<cudaEvent_t>& evs = h->iter_events;
-    while ((int)evs.size() < 2 * std::min(iters, 512)) {
+    while ((int)evs.size() < 5 * std::min(iters, 512)) {
         cudaEvent_t e;
         CUDA_TRY(cudaEventCreate(&e));
         evs.push_back(e);
     }
-    const bool phases = getenv("DESC_B200_PHASES") != nullptr && stream;
-    cudaEvent_t pev[3] = {nullptr, nullptr, nullptr};
-    if (phases)
-        for (auto& e : pev) cudaEventCreate(&e);
     int t_done = 0;
     bool stopped = false;
     const int check_every = 8;
@@ -964,14 +960,14 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
             a.corr2 = 1.0 - std::pow(rule->beta_2, (double)tcall);
         }
         const bool timed = t <= 512;
-        if (timed) CUDA_TRY(cudaEventRecord(evs[2 * (t - 1)], st));
+        if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1)], st));
         if (stream) {
             // pass 1 (smaller endpoints): update; pass 2 (larger endpoints) needs all of S_t
             ba.p = a;
             DESC_TRY(launch_stream_any(h, ba, adam ? 1 : 0));
-            if (phases && t == 10) cudaEventRecord(pev[0], st);
+            if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 1], st));
             if (h->world > 1) DESC_TRY(desc_allgather_ranges(h, h->S[nxt], sizeof(double), h->shard_edges));
-            if (phases && t == 10) cudaEventRecord(pev[1], st);
+            if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 2], st));
             DESC_TRY(launch_passb(h, ba, h->w[nxt]));
             k_pgd_partials<<<1, 256, 0, st>>>(h->pgd_partial, h->v_end - h->v_begin, h->d_ctrl, h->acc[nxt] + 2 * m);
             KERNEL_CHECK(h);
@@ -984,24 +980,20 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
         } else {
             DESC_TRY(launch_iter_any(h, a, adam ? 1 : 0));
         }
-        if (timed) CUDA_TRY(cudaEventRecord(evs[2 * (t - 1) + 1], st));
+        if (timed) {
+            if (!stream) {   // single-phase paths: no events inside
+                CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 1], st));
+                CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 2], st));
+            }
+            CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 3], st));
+        }
         if (h->world > 1) {
             DESC_TRY(desc_allreduce_sum(h, h->acc[nxt], nacc));
             if (!stream) DESC_TRY(desc_allgather_ranges(h, h->S[nxt], sizeof(double), h->shard_edges));
         }
+        if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 4], st));
         k_pgd_finalize<<<1, 1, 0, st>>>(h->acc[nxt] + 2 * m, t, 0, m, 1e-5, 30, h->d_hist, h->d_ctrl, h->d_ctrl_f);
         KERNEL_CHECK(h);
-        if (phases && t == 10 && timed) {   // DESC_B200_PHASES: where does iteration 10 spend its time?
-            cudaEventRecord(pev[2], st);
-            cudaEventSynchronize(pev[2]);
-            float a1 = 0, a2 = 0, a3 = 0, a4 = 0;
-            cudaEventElapsedTime(&a1, evs[2 * (t - 1)], pev[0]);
-            cudaEventElapsedTime(&a2, pev[0], pev[1]);
-            cudaEventElapsedTime(&a3, pev[1], evs[2 * (t - 1) + 1]);
-            cudaEventElapsedTime(&a4, evs[2 * (t - 1) + 1], pev[2]);
-            fprintf(stderr, "[desc_b200 rank %d] iteration 10: pass1 %.3f ms | allgather S %.3f | pass2 %.3f | allreduce+finalize %.3f\n",
-                    h->rank, a1, a2, a3, a4);
-        }
         t_done = t;
         if (t % check_every == 0 || t == iters) {
             CUDA_TRY(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1043,17 +1035,24 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
     h->have_pgd = true;
     *iters_run = final_iter;
     rule->t += final_iter;
-    // mean duration of the iteration kernels over the iterations that did real work
-    double sum_ms = 0.0;
+    // mean durations over the iterations that did real work: kernels of pass 1 / pass 2, collectives
+    double s1 = 0.0, s2 = 0.0, sc = 0.0;
     int cnt = 0;
     for (int t = 1; t <= std::min(std::min(t_done, 512), std::max(final_iter, 1)); t++) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, evs[2 * (t - 1)], evs[2 * (t - 1) + 1]) == cudaSuccess) {
-            sum_ms += ms;
+        float a1 = 0.f, ag = 0.f, a2 = 0.f, ar = 0.f;
+        cudaEvent_t* e = &evs[5 * (t - 1)];
+        if (cudaEventElapsedTime(&a1, e[0], e[1]) == cudaSuccess && cudaEventElapsedTime(&ag, e[1], e[2]) == cudaSuccess &&
+            cudaEventElapsedTime(&a2, e[2], e[3]) == cudaSuccess && cudaEventElapsedTime(&ar, e[3], e[4]) == cudaSuccess) {
+            s1 += a1;
+            s2 += a2;
+            sc += ag + ar;
             cnt++;
         }
     }
+    h->tm.pgd_pass1_ms = cnt > 0 ? s1 / cnt : 0.0;
+    h->tm.pgd_pass2_ms = cnt > 0 ? s2 / cnt : 0.0;
+    h->tm.pgd_comm_ms = cnt > 0 ? sc / cnt : 0.0;
+    h->tm.pgd_iter_ms = cnt > 0 ? (s1 + s2) / cnt : 0.0;
     h->tm.pgd_launches = h->launches - launches0;
-    h->tm.pgd_iter_ms = cnt > 0 ? sum_ms / cnt : 0.0;
     return DESC_B200_OK;
 }

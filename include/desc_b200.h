@@ -89,11 +89,14 @@ typedef struct desc_b200_timings {
     double pgd_ms;        /* pgd: all iterations actually run                                */
     double gcw_ms;        /* gcw: weights, power iteration, projection                       */
     double d2h_ms;        /* device->host copies of results of the last pgd/gcw call         */
-    double pgd_iter_ms;   /* mean duration of one fused PGD iteration kernel                 */
+    double pgd_iter_ms;   /* mean duration of the kernels of one PGD iteration (pass 1 + pass 2) */
     int32_t pgd_launches; /* kernels launched by the last pgd call                           */
     int32_t gcw_iters;    /* power iterations of the last gcw call                           */
     int32_t total_launches; /* kernels launched by this handle so far                        */
     int32_t reserved;
+    double pgd_pass1_ms;  /* mean duration of the update kernel (pass over smaller endpoints) */
+    double pgd_pass2_ms;  /* mean duration of the pass over larger endpoints (0: single-kernel paths) */
+    double pgd_comm_ms;   /* mean per-iteration time in collectives (all-gather S + all-reduce sums) */
 } desc_b200_timings;
 
 const char* desc_b200_last_error(void);
