@@ -385,6 +385,8 @@ struct FillArgs {
     int64_t slot_base;
     int n_sample, maxc;
     uint64_t seed;
+    uint64_t* thr_key;      // per-edge sampler threshold (largest selected key, its apex); may be null
+    int* thr_k;
 };
 
 __global__ void k_fill_slots(FillArgs a) {
@@ -429,20 +431,67 @@ __global__ void k_fill_slots(FillArgs a) {
         }
         __syncwarp();
         const bool sample = c > a.n_sample;  // len==n_sample keeps everything (DESC.m:83)
+        uint64_t tkey = ~0ull;               // threshold of an unsampled list: everything is a member
+        int tk = 0x7fffffff;
         if (sample) {
-            for (int q = lane; q < c; q += 32) ckey[q] = desc_key(a.seed, (uint64_t)e, (uint64_t)ck[q]);
-            __syncwarp();
+            // keep the n_sample smallest (key, apex) pairs: MSB-first radix selection over the 64-bit keys.
+            // csel: 0 = rejected, 1 = selected, 2 = undecided.  ~log2(c)+4 rounds instead of c^2/32 compares.
             for (int q = lane; q < c; q += 32) {
-                const uint64_t kq = ckey[q];
-                const int vq = ck[q];
-                int rank = 0;
-                for (int r = 0; r < c; r++) {
-                    uint64_t kr = ckey[r];
-                    rank += (kr < kq) || (kr == kq && ck[r] < vq);
-                }
-                csel[q] = rank < a.n_sample;
+                ckey[q] = desc_key(a.seed, (uint64_t)e, (uint64_t)ck[q]);
+                csel[q] = 2;
             }
             __syncwarp();
+            int need = a.n_sample, und = c;
+            for (int bit = 63; bit >= 0 && need > 0 && und > need; bit--) {
+                int cnt0 = 0;
+                for (int q = lane; q < c; q += 32) cnt0 += (csel[q] == 2) && !((ckey[q] >> bit) & 1ull);
+                cnt0 = __reduce_add_sync(0xffffffffu, cnt0);
+                if (cnt0 <= need) {   // all undecided keys with a 0 bit are among the smallest
+                    for (int q = lane; q < c; q += 32)
+                        if (csel[q] == 2 && !((ckey[q] >> bit) & 1ull)) csel[q] = 1;
+                    need -= cnt0;
+                    und -= cnt0;
+                } else {              // the n_sample-th smallest has a 0 bit: keys with a 1 bit are out
+                    for (int q = lane; q < c; q += 32)
+                        if (csel[q] == 2 && ((ckey[q] >> bit) & 1ull)) csel[q] = 0;
+                    und = cnt0;
+                }
+                __syncwarp();
+            }
+            // the rest: exactly `need` undecided keys left, or equal keys (smallest apices first: the
+            // candidates are in ascending apex order)
+            int taken = 0;
+            for (int qb = 0; qb < c; qb += 32) {
+                const int q = qb + lane;
+                const bool u = q < c && csel[q] == 2;
+                const unsigned bal = __ballot_sync(0xffffffffu, u);
+                if (u) csel[q] = (taken + __popc(bal & ((1u << lane) - 1u))) < need ? 1 : 0;
+                taken += __popc(bal);
+            }
+            __syncwarp();
+            // threshold = largest selected (key, apex)
+            uint64_t mk = 0ull;
+            int mv = -1;
+            for (int q = lane; q < c; q += 32)
+                if (csel[q] == 1 && (ckey[q] > mk || (ckey[q] == mk && ck[q] > mv))) {
+                    mk = ckey[q];
+                    mv = ck[q];
+                }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const uint64_t ok = __shfl_xor_sync(0xffffffffu, mk, o);
+                const int ov = __shfl_xor_sync(0xffffffffu, mv, o);
+                if (ok > mk || (ok == mk && ov > mv)) {
+                    mk = ok;
+                    mv = ov;
+                }
+            }
+            tkey = mk;
+            tk = mv;
+        }
+        if (a.thr_key && lane == 0) {
+            a.thr_key[e] = tkey;
+            a.thr_k[e] = tk;
         }
         // compaction + output
         const int64_t r0 = a.rowptr[e];
@@ -450,7 +499,7 @@ __global__ void k_fill_slots(FillArgs a) {
         int outpos = 0;
         for (int qb = 0; qb < c; qb += 32) {
             int q = qb + lane;
-            bool sel = q < c && (!sample || csel[q]);
+            bool sel = q < c && (!sample || csel[q] == 1);
             unsigned bal = __ballot_sync(0xffffffffu, sel);
             if (sel) {
                 int p = outpos + __popc(bal & ((1u << lane) - 1u));
@@ -552,6 +601,38 @@ __global__ void k_recip_flags(const int* __restrict__ ei, const int* __restrict_
                              : apex_lsearch(apex, rowptr[eik], rowptr[eik + 1], j);
             bool fb = SORTED ? apex_bsearch(apex, rowptr[ejk], rowptr[ejk + 1], i)
                              : apex_lsearch(apex, rowptr[ejk], rowptr[ejk + 1], i);
+            pk_ki[s - slot_base] = (pki & ~PK_APP) | (fa ? PK_APP : 0u);
+            pk_jk[s - slot_base] = (pjk & ~PK_APP) | (fb ? PK_APP : 0u);
+            if (rk_i) {
+                rk_i[s - slot_base] = (uint16_t)((rk_i[s - slot_base] & RK_MASK) | (fa ? RK_APP : 0u) | (fb ? RK_APP2 : 0u));
+                rk_j[s - slot_base] = (uint16_t)((rk_j[s - slot_base] & RK_MASK) | (fb ? RK_APP : 0u));
+            }
+        }
+    }
+}
+
+// Reciprocal-slot flags for the hash sampler (DESC.m:98-127): apex j is in the sampled list of edge
+// {i,k} iff (key(seed, e_ik, j), j) <= that edge's threshold pair: two table lookups per slot instead
+// of two binary searches in the partner edges' apex lists.
+__global__ void k_recip_flags_thr(const int* __restrict__ ei, const int* __restrict__ ej,
+                                  const int64_t* __restrict__ rowptr, uint32_t* __restrict__ pk_jk,
+                                  uint32_t* __restrict__ pk_ki, uint16_t* __restrict__ rk_i,
+                                  uint16_t* __restrict__ rk_j, const uint64_t* __restrict__ thr_key,
+                                  const int* __restrict__ thr_k, uint64_t seed, int64_t l0, int64_t l1,
+                                  int64_t slot_base) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t e = l0 + warp; e < l1; e += nwarps) {
+        const int i = ei[e], j = ej[e];
+        const int64_t r0 = rowptr[e], r1 = rowptr[e + 1];
+        for (int64_t s = r0 + lane; s < r1; s += 32) {
+            const uint32_t pki = pk_ki[s - slot_base], pjk = pk_jk[s - slot_base];
+            const int64_t eik = pki & PK_MASK, ejk = pjk & PK_MASK;
+            const uint64_t ka = desc_key(seed, (uint64_t)eik, (uint64_t)j), ta = thr_key[eik];
+            const uint64_t kb = desc_key(seed, (uint64_t)ejk, (uint64_t)i), tb = thr_key[ejk];
+            const bool fa = ka < ta || (ka == ta && j <= thr_k[eik]);
+            const bool fb = kb < tb || (kb == tb && i <= thr_k[ejk]);
             pk_ki[s - slot_base] = (pki & ~PK_APP) | (fa ? PK_APP : 0u);
             pk_jk[s - slot_base] = (pjk & ~PK_APP) | (fb ? PK_APP : 0u);
             if (rk_i) {
@@ -807,6 +888,8 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
     fa.n_sample = h->n_sample;
     fa.maxc = std::max(maxc, 1);
     fa.seed = seed;
+    fa.thr_key = nullptr;
+    fa.thr_k = nullptr;
     if (h->m_cycle > 0) {
         if (explicit_lists) {
             CUDA_TRY(cudaMemcpyAsync(h->apex, cyc_apex, h->m_cycle * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -831,12 +914,23 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
             const size_t smem = per_warp * wpb;
             CUDA_TRY(cudaFuncSetAttribute(k_fill_slots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(smem, 1)));
+            if (!h->thr_key) {
+                CUDA_TRY(cudaMalloc(&h->thr_key, (size_t)m * sizeof(uint64_t)));
+                CUDA_TRY(cudaMalloc(&h->thr_k, (size_t)m * sizeof(int)));
+            }
+            fa.thr_key = h->thr_key;
+            fa.thr_k = h->thr_k;
             k_fill_slots<<<DESC_SMS * ctas_per_sm, wpb * 32, smem, st>>>(fa);
             KERNEL_CHECK(h);
-            // reciprocal flags need every edge's apex list
+            // every rank needs every edge's apex list (getters, explicit replays) and sampler threshold
             DESC_TRY(desc_allgather_ranges(h, h->apex, sizeof(int), h->shard_slots));
+            DESC_TRY(desc_allgather_ranges(h, h->thr_key, sizeof(uint64_t), h->shard_edges));
+            DESC_TRY(desc_allgather_ranges(h, h->thr_k, sizeof(int), h->shard_edges));
         }
-        if (h->apex_sorted)
+        if (!explicit_lists) {
+            k_recip_flags_thr<<<warp_grid, 256, 0, st>>>(h->ei, h->ej, h->rowptr, h->pk_jk, h->pk_ki, h->rk_i, h->rk_j,
+                                                         h->thr_key, h->thr_k, seed, h->e_begin, h->e_end, h->slot_base);
+        } else if (h->apex_sorted)
             k_recip_flags<true><<<warp_grid, 256, 0, st>>>(h->ei, h->ej, h->rowptr, h->apex, h->pk_jk, h->pk_ki,
                                                           h->rk_i, h->rk_j, h->e_begin, h->e_end, h->slot_base);
         else

@@ -89,6 +89,8 @@ struct desc_b200_handle {
     bool built = false, have_s0 = false, have_pgd = false;
     bool apex_sorted = true;
     int* codeg = nullptr;       // m
+    uint64_t* thr_key = nullptr;  // m: sampler threshold of every edge = largest selected (key, apex) pair;
+    int* thr_k = nullptr;         //    membership of an apex in an edge's sampled list is then one comparison
     int n_sample = 0, max_codeg = 0, max_ns = 0;
     int64_t m_pos = 0, m_cycle = 0;
     int64_t* rowptr = nullptr;  // m+1 over ALL edges (empty rows for edges without triangles)
