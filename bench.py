@@ -258,6 +258,13 @@ def run_gpu(args, wl):
     e2e = {"value": evals / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": (2 * m + 9 * m) * 8,
            "d2h_bytes_per_step": (m + 9 * wl["n"]) * 8, "ms_per_step": ms_e2e}
 
+    per_rank = None
+    if world > 1:   # per-rank kernel / collective times of the PGD iteration (load balance)
+        mine = [tm.get("pgd_pass1_ms", 0.0), tm.get("pgd_pass2_ms", 0.0), tm.get("pgd_comm_ms", 0.0)]
+        allv = [None] * world
+        dist.all_gather_object(allv, mine)
+        per_rank = {"pass1_ms": [round(v[0], 4) for v in allv], "pass2_ms": [round(v[1], 4) for v in allv],
+                    "comm_ms": [round(v[2], 4) for v in allv]}
     if rank == 0:
         peak, peak_src = measured_peak()
         local_slots = info["local_slots"]
@@ -294,7 +301,7 @@ def run_gpu(args, wl):
                 "stages_ms": {k: tm[k] for k in ("graph_ms", "build_ms", "cycle_ms", "pgd_ms", "gcw_ms", "pgd_iter_ms",
                                                  "pgd_pass1_ms", "pgd_pass2_ms", "pgd_comm_ms")},
                 "gcw_iters": tm["gcw_iters"], "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "cpu_baseline": cpu, "clocks": clocks}
+                "cpu_baseline": cpu, "clocks": clocks, "per_rank": per_rank}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

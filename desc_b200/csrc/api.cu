@@ -71,7 +71,7 @@ void desc_b200_destroy(desc_b200_handle* h) {
                     h->S[0], h->S[1], h->acc[0], h->acc[1], h->adam_m, h->adam_v, h->d_hist, h->d_ctrl,
                     h->d_ctrl_f, h->omega, h->isd, h->X[0], h->X[1], h->gcw_coef, h->gcw_red,
                     h->gcw_small, h->gcw_res, h->R_est, h->d_err, h->d_Sin, h->rk_i, h->rk_j, h->estart,
-                    h->pgd_partial, h->jhdr, h->sjk, h->thr_key, h->thr_k};
+                    h->pgd_partial, h->jhdr, h->sjk, h->thr_key, h->thr_k, h->comm_scratch};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);

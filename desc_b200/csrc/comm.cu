@@ -16,6 +16,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 
@@ -28,6 +29,8 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -58,6 +61,8 @@ int nccl_load() {
     LOAD(AllReduce, "ncclAllReduce");
     LOAD(Broadcast, "ncclBroadcast");
     LOAD(AllGather, "ncclAllGather");
+    LOAD(Send, "ncclSend");
+    LOAD(Recv, "ncclRecv");
     LOAD(GroupStart, "ncclGroupStart");
     LOAD(GroupEnd, "ncclGroupEnd");
     LOAD(GetErrorString, "ncclGetErrorString");
@@ -138,18 +143,95 @@ int desc_allreduce_sum(desc_b200_handle* h, double* buf, int64_t count) {
     return DESC_B200_OK;
 }
 
-// in-place ragged all-gather: rank r owns elements [bounds[r], bounds[r+1]) of buf
+// in-place ragged all-gather: rank r owns elements [bounds[r], bounds[r+1]) of buf.  Point-to-point
+// sends/receives in one group (all pairs move concurrently over NVSwitch) instead of `world`
+// broadcasts, which NCCL runs one after the other.
 int desc_allgather_ranges(desc_b200_handle* h, void* buf, size_t elem_bytes,
                           const std::vector<int64_t>& bounds) {
     if (h->world <= 1) return DESC_B200_OK;
+    const int me = h->rank;
+    char* mine = (char*)buf + (size_t)bounds[me] * elem_bytes;
+    const size_t my_bytes = (size_t)(bounds[me + 1] - bounds[me]) * elem_bytes;
     NCCL_TRY(g_nccl.GroupStart());
-    for (int r = 0; r < h->world; r++) {
-        const int64_t cnt = bounds[r + 1] - bounds[r];
-        if (cnt <= 0) continue;
-        char* p = (char*)buf + (size_t)bounds[r] * elem_bytes;
-        NCCL_TRY(g_nccl.Broadcast(p, p, (size_t)cnt * elem_bytes, ncclInt8, r, (ncclComm_t)h->comm, h->stream));
+    for (int d = 1; d < h->world; d++) {
+        const int to = (me + d) % h->world, from = (me - d + h->world) % h->world;
+        const size_t from_bytes = (size_t)(bounds[from + 1] - bounds[from]) * elem_bytes;
+        if (my_bytes > 0) NCCL_TRY(g_nccl.Send(mine, my_bytes, ncclInt8, to, (ncclComm_t)h->comm, h->stream));
+        if (from_bytes > 0)
+            NCCL_TRY(g_nccl.Recv((char*)buf + (size_t)bounds[from] * elem_bytes, from_bytes, ncclInt8, from,
+                                 (ncclComm_t)h->comm, h->stream));
     }
     NCCL_TRY(g_nccl.GroupEnd());
+    h->collectives++;
+    return DESC_B200_OK;
+}
+
+// sum over ranks of buf[bounds[r]*width .. bounds[r+1]*width) delivered to rank r only (a ragged
+// reduce-scatter), plus an all-reduce of the `tail` doubles at buf[total*width ..].  Every rank
+// sends its partial of range r to rank r and adds the received partials IN RANK ORDER: half the
+// bytes of an all-reduce, and a summation order that does not depend on NCCL's algorithm choice.
+__global__ void k_sum_partials(double* __restrict__ own, const double* __restrict__ scratch, int64_t count,
+                               int64_t stride, int world, int me) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double acc = 0.0;
+    int slot = 0;
+    for (int r = 0; r < world; r++) {
+        if (r == me)
+            acc += own[i];
+        else
+            acc += scratch[(int64_t)(slot++) * stride + i];
+    }
+    own[i] = acc;
+}
+
+int desc_reduce_to_owners(desc_b200_handle* h, double* buf, int width, const std::vector<int64_t>& bounds,
+                          int tail) {
+    if (h->world <= 1) return DESC_B200_OK;
+    const int me = h->rank, W = h->world;
+    const int64_t total = bounds[W];
+    int64_t maxr = 0;
+    for (int r = 0; r < W; r++) maxr = std::max<int64_t>(maxr, bounds[r + 1] - bounds[r]);
+    const int64_t stride = maxr * width + tail;            // doubles per received partial
+    const size_t need = (size_t)(W - 1) * stride * sizeof(double);
+    if (h->comm_scratch_bytes < need) {
+        if (h->comm_scratch) cudaFree(h->comm_scratch);
+        h->comm_scratch = nullptr;
+        CUDA_TRY(cudaMalloc(&h->comm_scratch, need));
+        h->comm_scratch_bytes = need;
+    }
+    double* scratch = (double*)h->comm_scratch;
+    const int64_t my_cnt = (bounds[me + 1] - bounds[me]) * width;
+    NCCL_TRY(g_nccl.GroupStart());
+    int slot_of[64];
+    {
+        int sl = 0;
+        for (int r = 0; r < W; r++) slot_of[r] = (r == me) ? -1 : sl++;
+    }
+    for (int d = 1; d < W; d++) {
+        const int to = (me + d) % W, from = (me - d + W) % W;
+        const int64_t to_cnt = (bounds[to + 1] - bounds[to]) * width;
+        if (to_cnt > 0)
+            NCCL_TRY(g_nccl.Send(buf + bounds[to] * width, (size_t)to_cnt, ncclFloat64, to, (ncclComm_t)h->comm, h->stream));
+        if (my_cnt > 0)
+            NCCL_TRY(g_nccl.Recv(scratch + (int64_t)slot_of[from] * stride, (size_t)my_cnt, ncclFloat64, from,
+                                 (ncclComm_t)h->comm, h->stream));
+        if (tail > 0) {
+            NCCL_TRY(g_nccl.Send(buf + total * width, (size_t)tail, ncclFloat64, to, (ncclComm_t)h->comm, h->stream));
+            NCCL_TRY(g_nccl.Recv(scratch + (int64_t)slot_of[from] * stride + maxr * width, (size_t)tail, ncclFloat64, from,
+                                 (ncclComm_t)h->comm, h->stream));
+        }
+    }
+    NCCL_TRY(g_nccl.GroupEnd());
+    if (my_cnt > 0) {
+        k_sum_partials<<<(unsigned)((my_cnt + 255) / 256), 256, 0, h->stream>>>(buf + bounds[me] * width, scratch, my_cnt,
+                                                                              stride, W, me);
+        KERNEL_CHECK(h);
+    }
+    if (tail > 0) {
+        k_sum_partials<<<1, 32, 0, h->stream>>>(buf + total * width, scratch + maxr * width, tail, stride, W, me);
+        KERNEL_CHECK(h);
+    }
     h->collectives++;
     return DESC_B200_OK;
 }

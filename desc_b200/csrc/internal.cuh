@@ -68,6 +68,8 @@ struct desc_b200_handle {
     bool own_stream = false;
     int rank = 0, world = 1;
     void* comm = nullptr;       // ncclComm_t (comm.cu)
+    void* comm_scratch = nullptr;   // receive buffer of desc_reduce_to_owners
+    size_t comm_scratch_bytes = 0;
     int launches = 0;
     int collectives = 0;
 
@@ -165,6 +167,8 @@ void desc_comm_destroy(desc_b200_handle* h);
 int desc_allreduce_sum(desc_b200_handle* h, double* buf, int64_t count);
 int desc_allgather_ranges(desc_b200_handle* h, void* buf, size_t elem_bytes,
                           const std::vector<int64_t>& bounds);
+int desc_reduce_to_owners(desc_b200_handle* h, double* buf, int width, const std::vector<int64_t>& bounds,
+                          int tail);
 
 // ---- device helpers -----------------------------------------------------------------
 #ifdef __CUDACC__

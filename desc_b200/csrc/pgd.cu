@@ -927,7 +927,7 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
     }
     if (h->world > 1) DESC_TRY(desc_allgather_ranges(h, h->S[0], sizeof(double), h->shard_edges));
     if (stream && h->n_slots > 0) DESC_TRY(launch_passb(h, ba, h->w[0]));   // needs every rank's S_0
-    if (h->world > 1) DESC_TRY(desc_allreduce_sum(h, h->acc[0], nacc));
+    if (h->world > 1) DESC_TRY(desc_reduce_to_owners(h, h->acc[0], 2, h->shard_edges, 2));
 
     // per-iteration kernel timing: events around the iteration kernels only
     std::vector<cudaEvent_t>& evs = h->iter_events;
@@ -988,7 +988,8 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
             CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 3], st));
         }
         if (h->world > 1) {
-            DESC_TRY(desc_allreduce_sum(h, h->acc[nxt], nacc));
+            // a rank reads only the partner sums of its own edges: deliver each range's sum to its owner
+            DESC_TRY(desc_reduce_to_owners(h, h->acc[nxt], 2, h->shard_edges, 2));
             if (!stream) DESC_TRY(desc_allgather_ranges(h, h->S[nxt], sizeof(double), h->shard_edges));
         }
         if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 4], st));
