@@ -349,3 +349,61 @@ def test_vertex_blocked_path_is_bit_reproducible():
     np.testing.assert_array_equal(a["S_vec"], b["S_vec"])
     np.testing.assert_array_equal(a["w"], b["w"])
     np.testing.assert_array_equal(a["hist"], b["hist"])
+
+
+def test_blocked_direct_load_path_still_matches_oracle(monkeypatch):
+    """k_pgd_block + k_pgd_scatter (same shared-memory tables, direct loads, L2 gather) is the fallback for
+    slot lists longer than the streamed kernel supports; force it and check parity"""
+    monkeypatch.setenv("DESC_B200_PGD_PATH", "blocked")
+    mo = O.uniform_topology(160, 0.5, 0.25, 0.1, "uniform", rng=33)
+    for ns in (0, 70):
+        c = run_cuda(mo["Ind"], mo["RijMat"], desc_b200.ConstantStepSize(0.02), 40, n_sample=ns, seed=8)
+        o = run_oracle(mo["Ind"], mo["RijMat"], O.ConstantStepSize(0.02), 40, n_sample=ns or None, seed=8)
+        assert_incidence_equal(c, o["inc"])
+        assert_solution_close(c, o)
+
+
+_ORACLE_CACHE = {}
+
+
+def _cached_case(n, p, rng, lr, iters, ns, seed):
+    key = (n, p, rng, lr, iters, ns, seed)
+    if key not in _ORACLE_CACHE:
+        mo = O.uniform_topology(n, p, 0.2, 0.1, "uniform", rng=rng)
+        o = run_oracle(mo["Ind"], mo["RijMat"], O.ConstantStepSize(lr), iters, n_sample=(None if ns == 0 else ns),
+                       seed=seed, gcw=False)
+        _ORACLE_CACHE[key] = (mo, o)
+    return _ORACLE_CACHE[key]
+
+
+@pytest.mark.parametrize("shape", ["8,4,4,2", "8,4,2,2", "4,8,2,2"])
+@pytest.mark.parametrize("ns", [0, 45, 100])
+def test_streamed_path_launch_shapes_and_slot_list_lengths(monkeypatch, shape, ns):
+    """every compiled (slots per lane, compute warps, scatter warps) shape of the TMA-streamed kernel, with
+    slot lists of <=32, <=64 and <=128 entries (4..16 or 8..32 lanes per edge), against the oracle"""
+    monkeypatch.setenv("DESC_B200_ST", shape)
+    mo, o = _cached_case(240, 0.65, 34, 0.05, 20, ns, 4)
+    c = run_cuda(mo["Ind"], mo["RijMat"], desc_b200.ConstantStepSize(0.05), 20, n_sample=ns, seed=4, gcw=False)
+    assert c["info"]["max_slots_per_edge"] > (0 if ns == 0 else 32)
+    assert_incidence_equal(c, o["inc"])
+    assert_solution_close(c, o)
+
+
+def test_streamed_path_slot_lists_up_to_256():
+    """all triangles of a dense graph (co-degrees above 128): the widest lanes-per-edge instantiation"""
+    mo, o = _cached_case(380, 0.62, 36, 0.05, 6, -1, 4)
+    c = run_cuda(mo["Ind"], mo["RijMat"], desc_b200.ConstantStepSize(0.05), 6, n_sample=-1, seed=4, gcw=False)
+    assert 128 < c["info"]["max_slots_per_edge"] <= 256
+    np.testing.assert_array_equal(c["apex"], o["inc"].k)          # (n_sample is reported differently for "all")
+    np.testing.assert_array_equal(c["ikj"], o["inc"].IKJ >= 0)
+    assert_solution_close(c, o)
+
+
+def test_second_pass_tma_variant_matches_oracle(monkeypatch):
+    """DESC_B200_PASSB=tma: the pass over larger endpoints fed by per-edge bulk copies"""
+    monkeypatch.setenv("DESC_B200_PASSB", "tma")
+    mo = O.uniform_topology(200, 0.5, 0.2, 0.1, "uniform", rng=35)
+    for ns in (0, 40):
+        c = run_cuda(mo["Ind"], mo["RijMat"], desc_b200.ConstantStepSize(0.02), 30, n_sample=ns, seed=2, gcw=False)
+        o = run_oracle(mo["Ind"], mo["RijMat"], O.ConstantStepSize(0.02), 30, n_sample=ns or None, seed=2, gcw=False)
+        assert_solution_close(c, o)
