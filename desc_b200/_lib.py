@@ -22,7 +22,7 @@ ERROR_NAMES = {ERR_ARG: "DESC_B200_ERR_ARG", ERR_CUDA: "DESC_B200_ERR_CUDA", ERR
 SYMBOLS = [
     "desc_b200_last_error", "desc_b200_version", "desc_b200_device_count", "desc_b200_nccl_unique_id", "desc_b200_comm_finalize", "desc_b200_trim",
     "desc_b200_create", "desc_b200_destroy", "desc_b200_build_incidence", "desc_b200_cycle_inconsistency",
-    "desc_b200_pgd", "desc_b200_gcw", "desc_b200_solve", "desc_b200_get_info", "desc_b200_get_codeg",
+    "desc_b200_pgd", "desc_b200_gcw", "desc_b200_refine", "desc_b200_solve", "desc_b200_get_info", "desc_b200_get_codeg",
     "desc_b200_get_incidence", "desc_b200_get_slots", "desc_b200_get_s0", "desc_b200_get_w",
     "desc_b200_get_gcw_info", "desc_b200_get_timings", "desc_b200_sync",
 ]
@@ -51,7 +51,7 @@ class Timings(C.Structure):
                 ("pgd_ms", C.c_double), ("gcw_ms", C.c_double), ("d2h_ms", C.c_double), ("pgd_iter_ms", C.c_double),
                 ("pgd_launches", C.c_int32), ("gcw_iters", C.c_int32), ("total_launches", C.c_int32),
                 ("reserved", C.c_int32), ("pgd_pass1_ms", C.c_double), ("pgd_pass2_ms", C.c_double),
-                ("pgd_comm_ms", C.c_double)]
+                ("pgd_comm_ms", C.c_double), ("laa_ms", C.c_double), ("laa_iters", C.c_int32), ("laa_cg_iters", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -83,6 +83,7 @@ def load():
     lib.desc_b200_cycle_inconsistency.argtypes = [vp]
     lib.desc_b200_pgd.argtypes = [vp, i32, C.POINTER(StepRule), dp, dp, C.POINTER(i32)]
     lib.desc_b200_gcw.argtypes = [vp, dp, dp]
+    lib.desc_b200_refine.argtypes = [vp, dp, dp, dp, C.POINTER(i32), dp]
     lib.desc_b200_solve.argtypes = [vp, i32, u64, i32, C.POINTER(StepRule), dp, dp, dp, C.POINTER(i32)]
     lib.desc_b200_get_info.argtypes = [vp, C.POINTER(i64)]
     lib.desc_b200_get_codeg.argtypes = [vp, vp]

@@ -252,6 +252,54 @@ int desc_b200_gcw(desc_b200_handle* h, const double* S_vec, double* R_out) {
     return DESC_B200_OK;
 }
 
+int desc_b200_refine(desc_b200_handle* h, const double* S_vec, const double* R_init, double* R_out,
+                     int32_t* iters_run, double* scores) {
+    DESC_TRY(check_handle(h));
+    const double* d_S = nullptr;
+    if (S_vec) {
+        if (!h->d_Sin) CUDA_TRY(cudaMalloc(&h->d_Sin, h->m * sizeof(double)));
+        CUDA_TRY(cudaMemcpyAsync(h->d_Sin, S_vec, h->m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        d_S = h->d_Sin;
+    } else {
+        if (!h->have_pgd) {
+            desc_set_error("refine with S_vec=NULL needs a previous pgd on this handle");
+            return DESC_B200_ERR_STATE;
+        }
+        d_S = h->S[h->final_buf];
+    }
+    double* d_R = nullptr;
+    if (R_init) {
+        CUDA_TRY(cudaMalloc(&d_R, 9 * (size_t)h->n * sizeof(double)));
+        CUDA_TRY(cudaMemcpyAsync(d_R, R_init, 9 * (size_t)h->n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    } else if (!h->have_gcw) {
+        desc_set_error("refine with R_init=NULL needs a previous gcw on this handle");
+        return DESC_B200_ERR_STATE;
+    }
+    double* d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, 9 * (size_t)h->n * sizeof(double)));
+    int run = 0, rc;
+    {
+        StageTimer t(h, &h->tm.laa_ms);
+        rc = desc_laa_impl(h, d_S, d_R ? d_R : h->R_est, d_out, 100, 1e-3, &run, scores);
+        if (rc == DESC_B200_OK) rc = t.stop();
+    }
+    if (rc == DESC_B200_OK && R_out) {
+        cudaError_t e = cudaMemcpyAsync(R_out, d_out, 9 * (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) {
+            desc_set_error("CUDA error %s copying the refined rotations", cudaGetErrorString(e));
+            rc = DESC_B200_ERR_CUDA;
+        }
+    }
+    cudaFree(d_out);
+    if (d_R) cudaFree(d_R);
+    if (iters_run) *iters_run = run;
+    h->tm.laa_iters = run;
+    h->tm.laa_cg_iters = h->laa_cg_iters;
+    h->tm.total_launches = h->launches;
+    return rc;
+}
+
 int desc_b200_solve(desc_b200_handle* h, int32_t n_sample, uint64_t seed, int32_t iters,
                     desc_b200_step_rule* rule, double* S_vec_out, double* R_out, double* hist_out,
                     int32_t* iters_run_out) {

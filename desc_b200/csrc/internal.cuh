@@ -145,6 +145,7 @@ struct desc_b200_handle {
     double* R_est = nullptr;    // 9n
     double* d_Sin = nullptr;    // m: S_vec passed to gcw from the host
     bool have_gcw = false;
+    int laa_cg_iters = 0;       // CG iterations of the last refine call
 
     // scratch ---------------------------------------------------------------------------
     int* d_err = nullptr;       // device error flags
@@ -159,6 +160,8 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample, uint64_t seed,
 int desc_cycle_impl(desc_b200_handle* h);
 int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int* iters_run);
 int desc_gcw_impl(desc_b200_handle* h, const double* d_S);
+int desc_laa_impl(desc_b200_handle* h, const double* d_S, const double* d_Rinit, double* d_Rout, int max_iters,
+                  double stop_threshold, int* iters_run, double* scores_host);
 int desc_exclusive_scan_i64(desc_b200_handle* h, const int* in, int64_t* out, int64_t count);
 
 // multi-GPU collectives (comm.cu); no-ops when world==1

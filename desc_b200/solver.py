@@ -204,6 +204,24 @@ class Solver:
         _lib.check(self._lib.desc_b200_gcw(self._h, _ptr(S), _ptr(R)))
         return R
 
+    def refine(self, S_vec=None, R_init=None):
+        """DESC step 5 (DESC.m:265-312): weighted Lie-algebraic averaging started from R_init (default: the
+        rotations of the last gcw) with S_vec (default: the last pgd).  Returns (R_est 3x3xn, scores)."""
+        info = self.info()
+        S = None if S_vec is None else np.ascontiguousarray(np.asarray(S_vec, dtype=np.float64).ravel())
+        if S is not None and S.size != self.m:
+            raise ValueError("S_vec must have m entries")
+        R0 = None
+        if R_init is not None:
+            R0 = np.asfortranarray(np.asarray(R_init, dtype=np.float64))
+            if R0.shape != (3, 3, info["n"]):
+                raise ValueError("R_init must be 3 x 3 x n")
+        R = np.empty((3, 3, info["n"]), dtype=np.float64, order="F")
+        scores = np.zeros(100, dtype=np.float64)
+        run = C.c_int32(0)
+        _lib.check(self._lib.desc_b200_refine(self._h, _ptr(S), _ptr(R0), _ptr(R), C.byref(run), _ptr(scores)))
+        return R, scores[:run.value].copy()
+
     # -- getters -------------------------------------------------------------------------
     def info(self):
         a = (C.c_int64 * 10)()
@@ -319,14 +337,33 @@ def DESC_init(Ind, RijMat, params, **solver_kw):
 
 
 def DESC(Ind, RijMat, params, **solver_kw):
-    """``[R_est, R_init, S_vec] = DESC(Ind, RijMat, params)`` (Algorithms/DESC.m:14).
-
-    R_init and S_vec come from the device hot path (DESC.m:14-263).  The Lie-algebraic
-    refinement that turns R_init into R_est (DESC.m:265-312, Weighted_LAA) is SURVEY 8(f)
-    "next #1" and is not built yet: this function raises rather than return an unrefined R_est.
-    """
-    raise NotImplementedError("DESC(): the Weighted-LAA refinement stage (DESC.m:265-312) is not implemented on the "
-                              "device yet; use DESC_init for (R_init, S_vec) = DESC.m:14-263")
+    """``[R_est, R_init, S_vec] = DESC(Ind, RijMat, params)`` (Algorithms/DESC.m:14): the hot path
+    (DESC.m:14-263) followed by the weighted Lie-algebraic refinement (DESC.m:265-312), all on the device."""
+    rule = _param(params, "Gradient")
+    if rule is None or not hasattr(rule, "_to_c"):
+        raise ValueError("params.Gradient must be a ConstantStepSize / PiecewiseStepSize / HybridGradient object")
+    if _param(params, "make_plots", False):
+        raise NotImplementedError("params.make_plots=true (per-iteration GCW diagnostics and figures, "
+                                  "DESC.m:235-239,315-344) is not part of the device hot path")
+    verbose = _param(params, "verbose", False)
+    s = Solver(Ind, RijMat, **solver_kw)
+    try:
+        s.build_incidence(n_sample=int(_param(params, "n_sample", 0) or 0), seed=int(_param(params, "seed", 0) or 0),
+                          cycles=_param(params, "cycles"))
+        s.cycle_inconsistency()
+        S_vec, hist, iters_run = s.pgd(int(_param(params, "iters")), rule)
+        R_init = s.gcw()
+        if verbose:
+            print("Rotation Initialized!")                   # DESC.m:283
+            print("Start DESC refinement ...")
+        R_est, scores = s.refine()
+        if verbose:
+            for t, sc in enumerate(scores):                  # DESC.m:305
+                print("Iter %d: ||\u0394R||= %f" % (t + 1, sc))
+            print("DONE!")                                   # DESC.m:313
+    finally:
+        s.close()
+    return R_est, R_init, S_vec.reshape(1, -1)
 
 
 def GCW(Ind, AdjMat, RijMat, S_vec, **solver_kw):

@@ -97,6 +97,9 @@ typedef struct desc_b200_timings {
     double pgd_pass1_ms;  /* mean duration of the update kernel (pass over smaller endpoints) */
     double pgd_pass2_ms;  /* mean duration of the pass over larger endpoints (0: single-kernel paths) */
     double pgd_comm_ms;   /* mean per-iteration time in collectives (all-gather S + all-reduce sums) */
+    double laa_ms;        /* refine: all IRLS iterations                                      */
+    int32_t laa_iters;    /* IRLS iterations of the last refine call                          */
+    int32_t laa_cg_iters; /* CG iterations (all IRLS iterations together) of the last refine  */
 } desc_b200_timings;
 
 const char* desc_b200_last_error(void);
@@ -169,6 +172,13 @@ int desc_b200_get_w(desc_b200_handle* h, double* wijk);
 /* last gcw call: info[0]=power iterations, [1]=final residual ||(N+I)/2 X - X H||_F,
    [2..4]=the three Ritz values of D^-1/2 (W o R) D^-1/2 (= eigenvalues of GCW.m:27), descending */
 int desc_b200_get_gcw_info(desc_b200_handle* h, double info[8]);
+/* DESC step 5 (DESC.m:265-312 + Utils/Weighted_LAA.m, Build_Amatrix.m, R2Q.m, q2R.m): iteratively
+   re-weighted Lie-algebraic averaging started from R_init.  S_vec = NULL: the S_vec of the last pgd
+   on this handle; R_init = NULL: the rotations of the last gcw (DESC.m:267).  R_out: 3x3xn.  scores
+   (may be NULL): the `score` the reference prints per iteration (DESC.m:305), at most 99 values.
+   Stops like the reference: score <= 1e-3 or 99 iterations (DESC.m:272,287).  One GPU only. */
+int desc_b200_refine(desc_b200_handle* h, const double* S_vec, const double* R_init, double* R_out,
+                     int32_t* iters_run, double* scores);
 int desc_b200_get_timings(desc_b200_handle* h, desc_b200_timings* t);
 /* synchronise the handle's stream (for callers timing from outside) */
 int desc_b200_sync(desc_b200_handle* h);

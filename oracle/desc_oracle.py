@@ -623,3 +623,154 @@ def DESC_init(Ind, RijMat, params, **kw):
     """Algorithms/DESC_init.m:14.  Returns (R_est, S_vec)."""
     S_vec = DESC_PGD(Ind, RijMat, params, **kw)
     return gcw(Ind, RijMat, S_vec), S_vec
+
+
+# --------------------------------------------------------------------------------------------
+# DESC step 5: weighted Lie-algebraic averaging refinement (Algorithms/DESC.m:265-312)
+# --------------------------------------------------------------------------------------------
+def matlab_quantile(x, p):
+    """MATLAB ``quantile(x, p)`` for a vector: sample quantiles at (k-0.5)/n, linear interpolation,
+    clamped to the extremes (used at DESC.m:276,301)."""
+    xs = np.sort(np.asarray(x, dtype=np.float64).ravel())
+    n = xs.size
+    pos = n * p + 0.5                      # 1-based fractional position
+    if pos <= 1.0:
+        return float(xs[0])
+    if pos >= n:
+        return float(xs[-1])
+    lo = int(math.floor(pos))
+    frac = pos - lo
+    return float(xs[lo - 1] + frac * (xs[lo] - xs[lo - 1]))
+
+
+def R2Q(Rot):
+    """Utils/R2Q.m:7-13.  Rot: (3,3,K) MATLAB layout -> (K,4) quaternions [cos(t/2), sin(t/2) axis]."""
+    q0 = (Rot[0, 0, :] + Rot[1, 1, :] + Rot[2, 2, :] - 1.0) / 2.0
+    qv = np.stack([Rot[2, 1, :] - Rot[1, 2, :], Rot[0, 2, :] - Rot[2, 0, :], Rot[1, 0, :] - Rot[0, 1, :]], axis=1) / 2.0
+    q0 = np.sqrt((q0 + 1.0) / 2.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        qv = (qv / q0[:, None]) / 2.0
+    return np.concatenate([q0[:, None], qv], axis=1)
+
+
+def q2R(q):
+    """Utils/q2R.m:1-24 for one quaternion -> 3x3 (identity when abs(abs(q0)-1) <= 1e-12)."""
+    c2 = q[0]
+    if abs(abs(c2) - 1.0) > 1e-12:
+        s2 = math.sqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3])
+        s = 2.0 * s2 * c2
+        c = 2.0 * c2 * c2 - 1.0
+        n1, n2, n3 = q[1] / s2, q[2] / s2, q[3] / s2
+        cc = 1.0 - c
+        n12, n23, n31 = n1 * n2 * cc, n2 * n3 * cc, n3 * n1 * cc
+        return np.array([[c + n1 * n1 * cc, n12 - n3 * s, n31 + n2 * s],
+                         [n12 + n3 * s, c + n2 * n2 * cc, n23 - n1 * s],
+                         [n31 - n2 * s, n23 + n1 * s, c + n3 * n3 * cc]])
+    return np.eye(3)
+
+
+def _qmul_lines(a0, av, b0, bv):
+    """the quaternion product pattern of Weighted_LAA.m:12-14,48-50: (a0 b0 - av.bv, a0 bv + b0 av + av x bv)
+    written as the reference writes it (``[a0.*b0 - sum(av.*bv), a0.*bv + b0.*av + cross]`` with
+    cross = [av2 bv3 - av3 bv2, av3 bv1 - av1 bv3, av1 bv2 - av2 bv1])."""
+    s = a0 * b0 - np.sum(av * bv, axis=1)
+    cr = np.stack([av[:, 1] * bv[:, 2] - av[:, 2] * bv[:, 1], av[:, 2] * bv[:, 0] - av[:, 0] * bv[:, 2],
+                   av[:, 0] * bv[:, 1] - av[:, 1] * bv[:, 0]], axis=1)
+    return s, a0[:, None] * bv + b0[:, None] * av + cr
+
+
+def build_amatrix(ei, ej, n):
+    """Utils/Build_Amatrix.m:6-14: m x (n-1) signed incidence, node 1 grounded: -1 at i, +1 at j."""
+    import scipy.sparse as sp
+    m = ei.size
+    rows = np.concatenate([np.arange(m), np.arange(m)])
+    cols = np.concatenate([ei, ej]) - 1              # 0-based node -> column (node 0 dropped)
+    vals = np.concatenate([-np.ones(m), np.ones(m)])
+    keep = cols >= 0
+    return sp.csr_matrix((vals[keep], (rows[keep], cols[keep])), shape=(m, n - 1))
+
+
+def weighted_laa(ei, ej, Q, QQ, A, Weights):
+    """Utils/Weighted_LAA.m:4-52.  One weighted Lie-algebraic averaging step.
+    Returns (Q_new, W, B, score) exactly as the reference does (W is the QUATERNION of the update,
+    which is what DESC.m:290 multiplies with the A matrix)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    N = Q.shape[0]
+    # w = Qij * Qi   (:12-14)
+    s, v = _qmul_lines(QQ[:, 0], QQ[:, 1:4], Q[ei, 0], Q[ei, 1:4])
+    # w = inv(Qj) * w  (:17-19): scalar -Qj0 w0 - Qjv.wv ; vector -Qj0 wv + w0 Qjv + Qjv x wv
+    Qj0, Qjv = Q[ej, 0], Q[ej, 1:4]
+    s2_ = -Qj0 * s - np.sum(Qjv * v, axis=1)
+    cr = np.stack([Qjv[:, 1] * v[:, 2] - Qjv[:, 2] * v[:, 1], Qjv[:, 2] * v[:, 0] - Qjv[:, 0] * v[:, 2],
+                   Qjv[:, 0] * v[:, 1] - Qjv[:, 1] * v[:, 0]], axis=1)
+    v2 = (-Qj0)[:, None] * v + s[:, None] * Qjv + cr
+    s2 = np.sqrt(np.sum(v2 * v2, axis=1))                      # (:22)
+    th = 2.0 * np.arctan2(s2, s2_)                             # (:23)
+    th = np.where(th < -math.pi, th + 2 * math.pi, th)         # (:24)
+    th = np.where(th >= math.pi, th - 2 * math.pi, th)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        B = v2 * (th / s2)[:, None]                            # (:25)
+    B[np.isnan(B)] = 0.0                                       # (:36)
+    # weighted least squares (diag(W) A) \ (W .* B)  (:40), via the normal equations (unique solution)
+    WA = sp.diags(Weights) @ A
+    lhs = (WA.T @ WA).tocsc()
+    rhs = WA.T @ (Weights[:, None] * B)
+    X = spla.splu(lhs).solve(rhs)
+    W = np.zeros((N, 4))
+    W[0, :] = [1.0, 0.0, 0.0, 0.0]                             # (:38)
+    W[1:, 1:4] = X
+    score = float(np.sum(np.sqrt(np.sum(W[1:, 1:4] ** 2, axis=1))) / N)   # (:42)
+    theta = np.sqrt(np.sum(W[:, 1:4] ** 2, axis=1))            # (:44)
+    W[:, 0] = np.cos(theta / 2.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        W[:, 1:4] = W[:, 1:4] * (np.sin(theta / 2.0) / theta)[:, None]
+    W[np.isnan(W)] = 0.0                                       # (:48)
+    s3, v3 = _qmul_lines(Q[:, 0], Q[:, 1:4], W[:, 0], W[:, 1:4])   # Q = Q * W (:50-52)
+    return np.concatenate([s3[:, None], v3], axis=1), W, B, score
+
+
+def laa_refine(Ind, RijMat, S_vec, R_init, stop_threshold=1e-3, max_iters=100, quant_ratio_min=0.8,
+               weight_max=1e4, weight_min=1e-4, return_info=False):
+    """Algorithms/DESC.m:265-312: IRLS with weighted Lie-algebraic averaging, starting from R_init."""
+    n, ei, ej = check_ind(Ind)
+    S = np.asarray(S_vec, dtype=np.float64).ravel()
+    RR = np.transpose(np.asarray(RijMat, dtype=np.float64), (1, 0, 2))       # (:265)
+    A = build_amatrix(ei, ej, n)                                              # (:269)
+    Q = R2Q(np.asarray(R_init, dtype=np.float64))                             # (:270)
+    QQ = R2Q(RR)                                                              # (:271)
+    score, it = math.inf, 1
+    quant_ratio = 1.0
+    thresh = matlab_quantile(S, quant_ratio)                                  # (:276)
+    with np.errstate(divide="ignore"):
+        Weights = 1.0 / S ** 0.75                                             # (:278)
+    Weights[Weights > weight_max] = weight_max
+    Weights[S > thresh] = weight_min
+    scores = []
+    RSVec = S.copy()
+    while score > stop_threshold and it < max_iters:                         # (:287)
+        lam = 1.0 / (it + 1)
+        Q, W, B, score = weighted_laa(ei, ej, Q, QQ, A, Weights)
+        E = A @ W[1:, 1:4] - B                                                # (:290)
+        ResVec = np.sqrt(np.sum(E * E, axis=1)) / math.pi
+        RSVec = (1.0 - lam) * ResVec + lam * S
+        with np.errstate(divide="ignore"):
+            Weights = 1.0 / RSVec ** 0.75                                     # (:298)
+        quant_ratio = max(quant_ratio_min, quant_ratio - 0.05)
+        thresh = matlab_quantile(RSVec, quant_ratio)                          # (:301)
+        Weights[Weights > weight_max] = weight_max
+        Weights[RSVec > thresh] = weight_min
+        scores.append(score)
+        it += 1
+    R_est = np.zeros((3, 3, n))
+    for i in range(n):
+        R_est[:, :, i] = q2R(Q[i])                                            # (:309-312)
+    if return_info:
+        return R_est, dict(scores=np.array(scores), iterations=it - 1, RSVec=RSVec, Weights=Weights, thresh=thresh)
+    return R_est
+
+
+def DESC(Ind, RijMat, params, **kw):
+    """Algorithms/DESC.m:14.  Returns (R_est, R_init, S_vec)."""
+    R_init, S_vec = DESC_init(Ind, RijMat, params, **kw)
+    return laa_refine(Ind, RijMat, S_vec, R_init), R_init, S_vec

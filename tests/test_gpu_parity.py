@@ -407,3 +407,26 @@ def test_second_pass_tma_variant_matches_oracle(monkeypatch):
         c = run_cuda(mo["Ind"], mo["RijMat"], desc_b200.ConstantStepSize(0.02), 30, n_sample=ns, seed=2, gcw=False)
         o = run_oracle(mo["Ind"], mo["RijMat"], O.ConstantStepSize(0.02), 30, n_sample=ns or None, seed=2, gcw=False)
         assert_solution_close(c, o)
+
+
+@pytest.mark.parametrize("case", [(140, 0.5, 0.2, 0.1, 21), (120, 0.6, 0.3, 0.05, 22), (100, 0.5, 0.15, 0.0, 23)])
+def test_laa_refinement_matches_oracle(case):
+    """DESC step 5 (DESC.m:265-312): IRLS / weighted Lie-algebraic averaging on the device (CG on the
+    grounded weighted Laplacian, radix-select quantile) against the oracle (sparse direct solve, sort)."""
+    n, p, q, sigma, rng = case
+    mo = O.uniform_topology(n, p, q, sigma, "uniform", rng=rng)
+    oR_init, oS = O.DESC_init(mo["Ind"], mo["RijMat"], dict(iters=40, Gradient=O.ConstantStepSize(0.01)), seed=3)
+    oR, info = O.laa_refine(mo["Ind"], mo["RijMat"], oS, oR_init, return_info=True)
+    with desc_b200.Solver(mo["Ind"], mo["RijMat"]) as s:
+        R, scores = s.refine(S_vec=oS, R_init=oR_init)      # same inputs as the oracle: isolates the stage
+        t = s.timings()
+    assert len(scores) == info["iterations"] and t["laa_iters"] == info["iterations"]
+    np.testing.assert_allclose(scores, info["scores"], rtol=1e-8, atol=1e-12)
+    assert O.aligned_angle_deg(R, oR).mean() <= ROT_TOL_DEG
+    # the whole reference-style call
+    params = dict(iters=40, Gradient=desc_b200.ConstantStepSize(0.01), seed=3)
+    R_est, R_init, S_vec = desc_b200.DESC(mo["Ind"], mo["RijMat"], params)
+    assert R_est.shape == (3, 3, n) and R_init.shape == (3, 3, n) and S_vec.shape == (1, mo["Ind"].shape[0])
+    assert rel_err(S_vec.ravel(), oS, floor=1e-12) <= RTOL
+    assert O.aligned_angle_deg(R_init, oR_init).mean() <= ROT_TOL_DEG
+    assert O.aligned_angle_deg(R_est, oR).mean() <= 10 * ROT_TOL_DEG   # (R_init differs from the oracle's by its own 1e-6 deg)
