@@ -372,7 +372,7 @@ int laa_select(desc_b200_handle* h, const double* X, int64_t m, int64_t k, unsig
         int64_t cum = 0;
         int b = 0;
         for (; b < nb; b++) {
-            if (cum + hist[b] >= (uint64_t)k) break;
+            if (cum + (int64_t)hist[b] >= k) break;
             cum += hist[b];
         }
         if (b >= nb) {

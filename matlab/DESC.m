@@ -1,11 +1,16 @@
 function [R_est, R_init, S_vec] = DESC(Ind, RijMat, params)
 % Drop-in for Algorithms/DESC.m:14 -- what Demo/compare_algorithms.m:72 calls.
-% Stages 1-4 of the reference (DESC.m:14-263: incidence, d_ijk, PGD, GCW) run on the GPU.
-% Stage 5, the Lie-algebraic refinement (DESC.m:265-312), is delegated to desc_b200_refine, which
-% drives the reference's own host utilities (Utils/Weighted_LAA.m etc.) until the device version
-% (SURVEY 8(f) "next #1") lands.
+% Stages 1-4 of the reference (DESC.m:14-263: incidence, d_ijk, PGD, GCW) and stage 5, the weighted
+% Lie-algebraic refinement (DESC.m:265-312), all run on the GPU; this file only prints the
+% reference's progress lines.
     out    = desc_b200_run(Ind, RijMat, params, true);
     R_init = out.R_est;
     S_vec  = out.S_vec;
-    R_est  = desc_b200_refine(Ind, RijMat, R_init, S_vec);
+    disp('Rotation Initialized!'); disp('Start DESC refinement ...');      % DESC.m:283-284
+    ref    = desc_b200_mex('refine', Ind, RijMat, S_vec, R_init);
+    for it = 1:numel(ref.scores)
+        fprintf('Iter %d: ||\x394R||= %f\n', it, ref.scores(it));          % DESC.m:305
+    end
+    R_est = ref.R_est;
+    disp('DONE!');                                                          % DESC.m:313
 end

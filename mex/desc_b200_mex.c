@@ -3,6 +3,7 @@
  *
  *   out = desc_b200_mex('solve', Ind, RijMat, iters, rule, n_sample, seed, want_R)
  *   R   = desc_b200_mex('gcw',   Ind, RijMat, S_vec)
+ *   out = desc_b200_mex('refine', Ind, RijMat, S_vec, R_init)    (DESC.m:265-312; out.R_est, out.scores)
  *   n   = desc_b200_mex('device_count')
  *
  * 'solve' runs Algorithms/DESC.m:14-263 (== DESC_PGD.m:14-261 / DESC_init.m:14-253) on the GPU and
@@ -131,6 +132,36 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         plhs[0] = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
         fail_if(desc_b200_gcw(h, mxGetPr(prhs[3]), mxGetPr(plhs[0])), h);
         desc_b200_destroy(h);
+        return;
+    }
+    if (strcmp(cmd, "refine") == 0) {
+        if (nrhs != 5) mexErrMsgIdAndTxt("DESC:b200", "refine: 4 arguments expected");
+        mwSize m;
+        check_inputs(prhs[1], prhs[2], &m);
+        if (!mxIsDouble(prhs[3]) || mxGetNumberOfElements(prhs[3]) != m)
+            mexErrMsgIdAndTxt("DESC:b200", "S_vec must have one entry per edge");
+        desc_b200_handle* h = NULL;
+        fail_if(desc_b200_create(&h, 0, (int64_t)m, mxGetPr(prhs[1]), mxGetPr(prhs[2]), NULL), NULL);
+        int64_t info[10];
+        fail_if(desc_b200_get_info(h, info), h);
+        if (!mxIsDouble(prhs[4]) || mxGetNumberOfElements(prhs[4]) != (mwSize)(9 * info[0])) {
+            desc_b200_destroy(h);
+            mexErrMsgIdAndTxt("DESC:b200", "R_init must be 3 x 3 x n");
+        }
+        mwSize dims[3] = {3, 3, 0};
+        dims[2] = (mwSize)info[0];
+        mxArray* R = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
+        mxArray* sc = mxCreateDoubleMatrix(100, 1, mxREAL);
+        int32_t run = 0;
+        fail_if(desc_b200_refine(h, mxGetPr(prhs[3]), mxGetPr(prhs[4]), mxGetPr(R), &run, mxGetPr(sc)), h);
+        desc_b200_destroy(h);
+        mxArray* scores = mxCreateDoubleMatrix(run, 1, mxREAL);
+        for (int t = 0; t < run; t++) mxGetPr(scores)[t] = mxGetPr(sc)[t];
+        mxDestroyArray(sc);
+        const char* fields[] = {"R_est", "scores"};
+        plhs[0] = mxCreateStructMatrix(1, 1, 2, fields);
+        mxSetField(plhs[0], 0, "R_est", R);
+        mxSetField(plhs[0], 0, "scores", scores);
         return;
     }
     mexErrMsgIdAndTxt("DESC:b200", "unknown command '%s'", cmd);

@@ -141,3 +141,53 @@ def test_step_rules_follow_reference_formulas():
     h.stopAdam()
     s2 = h.GetStep(g)                                          # t=2 -> 100*lr/(fix(2/5)+1)
     np.testing.assert_allclose(s2, -1.0 * g)
+
+
+# ---- DESC step 5 (LAA refinement, DESC.m:265-312) ------------------------------------------
+def test_matlab_quantile_definition():
+    """MATLAB quantile: sample quantiles at (k-0.5)/n with linear interpolation, clamped"""
+    x = [5.0, 1.0, 3.0, 2.0, 4.0]
+    assert O.matlab_quantile(x, 0.5) == 3.0
+    assert O.matlab_quantile(x, 0.8) == 4.5
+    assert O.matlab_quantile(x, 0.95) == 5.0 and O.matlab_quantile(x, 1.0) == 5.0
+    assert O.matlab_quantile(x, 0.0) == 1.0 and O.matlab_quantile(x, 0.1) == 1.0
+    assert abs(O.matlab_quantile(x, 0.3) - 2.0) < 1e-15
+    assert abs(O.matlab_quantile([1.0, 2.0, 3.0, 4.0], 0.5) - 2.5) < 1e-15
+
+
+def test_r2q_q2r_round_trip_and_quaternion_product():
+    rng = np.random.default_rng(5)
+    R = O.to_matlab(O._rand_rot(20, rng))
+    Q = O.R2Q(R)
+    np.testing.assert_allclose(np.sum(Q * Q, axis=1), 1.0, atol=1e-14)
+    for v in range(20):
+        np.testing.assert_allclose(O.q2R(Q[v]), R[:, :, v], atol=1e-13)
+    np.testing.assert_array_equal(O.q2R(np.array([1.0, 0.0, 0.0, 0.0])), np.eye(3))
+    # the product pattern of Weighted_LAA.m composes rotations: q(Ra) * q(Rb) = q(Ra Rb)
+    s, v = O._qmul_lines(Q[:10, 0], Q[:10, 1:4], Q[10:, 0], Q[10:, 1:4])
+    for t in range(10):
+        np.testing.assert_allclose(O.q2R(np.concatenate([[s[t]], v[t]])), R[:, :, t] @ R[:, :, 10 + t], atol=1e-13)
+
+
+def test_build_amatrix_grounds_node_one():
+    A = O.build_amatrix(np.array([0, 0, 1]), np.array([1, 2, 2]), 3).toarray()
+    np.testing.assert_array_equal(A, [[1, 0], [0, 1], [-1, 1]])
+
+
+def test_laa_refine_known_answers():
+    """clean graph: the refinement leaves exact rotations exact; noisy graph: it stops by the score rule and
+    stays close to the ground truth; gauge: only the global right rotation of R_init carries over"""
+    mo = O.uniform_topology(40, 0.6, 0.0, 0.0, "uniform", rng=1)
+    S = np.full(mo["Ind"].shape[0], 1e-8)
+    R, info = O.laa_refine(mo["Ind"], mo["RijMat"], S, mo["R_orig"], return_info=True)
+    assert info["iterations"] == 1 and info["scores"][0] < 1e-7
+    assert O.rotation_alignment(R, mo["R_orig"])[2] < 1e-5
+    mo = O.uniform_topology(80, 0.5, 0.2, 0.05, "uniform", rng=2)
+    R0, S = O.DESC_init(mo["Ind"], mo["RijMat"], dict(iters=40, Gradient=O.ConstantStepSize(0.01)), seed=1)
+    R, info = O.laa_refine(mo["Ind"], mo["RijMat"], S, R0, return_info=True)
+    assert 1 <= info["iterations"] < 99 and info["scores"][-1] <= 1e-3
+    assert O.rotation_alignment(R, mo["R_orig"])[2] < 2.0
+    G = O._rand_rot(1, np.random.default_rng(3))[0]
+    R0g = np.stack([R0[:, :, v] @ G for v in range(R0.shape[2])], axis=2)
+    Rg = O.laa_refine(mo["Ind"], mo["RijMat"], S, R0g)
+    assert O.aligned_angle_deg(Rg, R).mean() < 1e-6
