@@ -79,6 +79,36 @@ def uniform_topology(n, p, q, sigma, model="uniform", seed=0, device="cuda"):
                 corrupted=corr)
 
 
+def ring_topology(n, deg, window, q, sigma, seed=0, device="cuda"):
+    """SfM-shaped graph for configs[4] of BASELINE.json (the reference has no such generator):
+    cameras on a closed track, node i is connected to each of the `window` following nodes (mod n)
+    independently with probability deg / (2 window), so the mean degree is `deg` and neighbours share
+    many neighbours (co-degree ~ (2 window - |i-j|) (deg / 2 window)^2), unlike an Erdos-Renyi graph of
+    the same density.  Rotations, corruption and noise as in ``uniform_topology`` ('uniform' model)."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    p = deg / (2.0 * window)
+    off = torch.arange(1, window + 1, device=device)
+    keep = torch.rand(n, window, generator=gen, device=device) < p
+    a = torch.arange(n, device=device)[:, None].expand(n, window)[keep]
+    b = (a + off[None, :].expand(n, window)[keep]) % n
+    lo, hi = torch.minimum(a, b), torch.maximum(a, b)
+    key = torch.unique(lo * n + hi)                       # sorted by (i, j), duplicates removed
+    ei, ej = key // n, key % n
+    m = ei.numel()
+    R_orig = _haar(n, gen, device)
+    Rij_orig = R_orig[ei] @ R_orig[ej].transpose(1, 2)
+    corr = torch.rand(m, generator=gen, device=device, dtype=torch.float64) < q
+    Rij = _polar(Rij_orig + sigma * torch.randn(m, 3, 3, generator=gen, device=device, dtype=torch.float64)) \
+        if sigma > 0 else Rij_orig.clone()
+    Rij[corr] = _haar(int(corr.sum()), gen, device)
+    tr = (Rij_orig * Rij).sum(dim=(1, 2))
+    ErrVec = torch.acos(((tr - 1) / 2).clamp(-1, 1)) / np.pi
+    Ind = torch.stack([ei + 1, ej + 1], dim=0).to(torch.float64).contiguous()
+    return dict(n=n, m=m, Ind=Ind, RijMat=Rij.transpose(1, 2).contiguous(),
+                R_orig=R_orig.transpose(1, 2).contiguous(), ErrVec=ErrVec, corrupted=corr)
+
+
 def to_host(model_out):
     """numpy views in the reference's shapes: Ind (m,2), RijMat (3,3,m), R_orig (3,3,n), ErrVec (m,)."""
     Ind = model_out["Ind"].cpu().numpy().T                       # (m, 2), Fortran-contiguous
