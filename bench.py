@@ -18,7 +18,7 @@ roofline = one PGD iteration = its two kernels (k_pgd_stream: update pass over s
          SURVEY 8d) / mean duration of the pair (CUDA events on the launching stream around each
          kernel) vs the measured HBM peak.  `traffic` = DRAM bytes of the pair from the committed ncu
          capture (profiles/), valid for the default workload on one GPU.
-cpu_baseline = the oracle port timed on this box's host cores on a bounded sample.
+cpu_baseline = the CPU restatement (oracle/) timed on this box's host cores on a bounded sample.
 """
 import argparse
 import json
@@ -99,18 +99,30 @@ class ClockSampler:
 # CPU baseline: the oracle port on a bounded sample of the workload
 # ------------------------------------------------------------------------------------------
 def cpu_sample(wl, n_sub, iters, seed=0):
-    """Oracle (numpy port of DESC.m / GCW.m) on the workload family at n_sub nodes with the same
-    edge density and sampling budget; returns evals/s over the whole solve, like `value`."""
-    import numpy as np
+    """CPU restatement of the reference on the workload family at n_sub nodes (same edge density and
+    sampling rule): numpy oracle for the incidence, d_ijk and GCW (1 thread), the C/OpenMP restatement
+    of the PGD loop (oracle/desc_pgd.c, DESC.m:148-261 statement by statement) on all host threads.
+    Returns whole-solve evals/s like `value`, the wall time and a description."""
     from oracle import desc_oracle as O
+    from oracle import desc_oracle_c as OC
+    threads = OC.max_threads()
     mo = O.uniform_topology(n_sub, wl["p"], wl["q"], wl["sigma"], wl["model"], rng=seed)
     t0 = time.perf_counter()
     inc = O.build_incidence(mo["Ind"], n_sample=None, seed=1)
     S0 = O.cycle_inconsistency(inc, mo["RijMat"])
-    S_vec, hist, iters_run = O.pgd(inc, S0, iters, O.ConstantStepSize(wl["lr"]))
+    t1 = time.perf_counter()
+    S_vec, hist, iters_run = OC.pgd(inc, S0, iters, O.ConstantStepSize(wl["lr"]), threads=threads)
+    t2 = time.perf_counter()
     O.gcw(mo["Ind"], mo["RijMat"], S_vec)
     dt = time.perf_counter() - t0
-    return inc.m_cycle * iters_run / dt, dt, dict(n=n_sub, m=int(inc.m), m_cycle=int(inc.m_cycle), iters=int(iters_run))
+    return inc.m_cycle * iters_run / dt, dt, dict(n=n_sub, m=int(inc.m), m_cycle=int(inc.m_cycle), iters=int(iters_run),
+                                                  threads=threads, pgd_s=t2 - t1,
+                                                  pgd_evals_per_s=inc.m_cycle * iters_run / (t2 - t1))
+
+
+CPU_SAMPLE_TEXT = ("CPU restatement of DESC.m:14-263 + GCW.m on the same graph family at n=%d (m=%d, m_cycle=%d), %d PGD "
+                   "iterations: numpy oracle for incidence / d_ijk / GCW (1 thread) + C/OpenMP PGD loop (%d threads, "
+                   "%.2e evals/s in the loop alone); %.1f s")
 
 
 def run_reference(args, wl):
@@ -127,13 +139,13 @@ def run_reference(args, wl):
         vals.append(v)
         times.append(dt)
     value = statistics.mean(vals)
-    sample = ("oracle port (numpy, oracle/desc_oracle.py) of DESC.m:14-263 + GCW.m on the same graph family at "
-              "n=%d (m=%d, m_cycle=%d), %d PGD iterations per step" % (info["n"], info["m"], info["m_cycle"], info["iters"]))
+    sample = CPU_SAMPLE_TEXT % (info["n"], info["m"], info["m_cycle"], info["iters"], info["threads"],
+                                info["pgd_evals_per_s"], statistics.mean(times))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(times),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"]},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["threads"], "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -286,9 +298,9 @@ def run_gpu(args, wl):
         cpu = None
         if world == 1 and not args.no_cpu:
             v, dt, ci = cpu_sample(wl, args.cpu_n, args.cpu_iters)
-            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": "numpy oracle port on the same graph family at n=%d (m=%d, m_cycle=%d), %d PGD iterations, "
-                             "%.1f s" % (ci["n"], ci["m"], ci["m_cycle"], ci["iters"], dt)}
+            cpu = {"value": v, "unit": UNIT, "cores": ci["threads"], "kind": "port",
+                   "sample": CPU_SAMPLE_TEXT % (ci["n"], ci["m"], ci["m_cycle"], ci["iters"], ci["threads"],
+                                                ci["pgd_evals_per_s"], dt)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -316,7 +328,7 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-n", type=int, default=1500, help="nodes of the CPU-baseline sample graph")
-    ap.add_argument("--cpu-iters", type=int, default=10, help="PGD iterations of the CPU-baseline sample")
+    ap.add_argument("--cpu-iters", type=int, default=100, help="PGD iterations of the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -191,3 +191,40 @@ def test_laa_refine_known_answers():
     R0g = np.stack([R0[:, :, v] @ G for v in range(R0.shape[2])], axis=2)
     Rg = O.laa_refine(mo["Ind"], mo["RijMat"], S, R0g)
     assert O.aligned_angle_deg(Rg, R).mean() < 1e-6
+
+
+# ---- C / OpenMP restatement of the PGD loop (oracle/desc_pgd.c) vs the numpy restatement ----------
+@pytest.mark.parametrize("rule_name", ["constant", "piecewise"])
+def test_c_restatement_of_pgd_matches_numpy_oracle(rule_name):
+    from oracle import desc_oracle_c as OC
+    mo = O.uniform_topology(90, 0.45, 0.25, 0.1, "uniform", rng=12)
+    inc = O.build_incidence(mo["Ind"], n_sample=12, seed=2)          # sampled lists: ~IKJ_appears occurs
+    S0 = O.cycle_inconsistency(inc, mo["RijMat"])
+    mk = (lambda: O.ConstantStepSize(0.03)) if rule_name == "constant" else (lambda: O.PiecewiseStepSize(0.2, 7))
+    ra, rb = mk(), mk()
+    S_a, h_a, k_a, w_a = O.pgd(inc, S0, 50, ra, return_w=True)
+    for threads in (1, 3):
+        rb = mk()
+        S_b, h_b, k_b, w_b = OC.pgd(inc, S0, 50, rb, threads=threads, return_w=True)
+        assert k_a == k_b
+        np.testing.assert_allclose(S_b, S_a, rtol=0, atol=1e-13)
+        np.testing.assert_allclose(w_b, w_a, rtol=0, atol=1e-13)
+        np.testing.assert_allclose(h_b[:, 1], h_a[:, 1], rtol=1e-11)
+    if rule_name == "piecewise":
+        assert rb.t == ra.t == k_a
+
+
+def test_c_restatement_early_stop_and_edges_without_cycles():
+    from oracle import desc_oracle_c as OC
+    mo = O.uniform_topology(60, 0.5, 0.0, 0.0, "uniform", rng=13)    # clean graph: objective ~0, stops by patience
+    inc = O.build_incidence(mo["Ind"], n_sample=None, seed=0)
+    S0 = O.cycle_inconsistency(inc, mo["RijMat"])
+    a = O.pgd(inc, S0, 80, O.ConstantStepSize(0.01))
+    b = OC.pgd(inc, S0, 80, O.ConstantStepSize(0.01))
+    assert a[2] == b[2] < 80
+    np.testing.assert_allclose(b[0], a[0], atol=1e-13)
+    Ind = np.array([[1, 2], [1, 3], [2, 3], [3, 4]], dtype=np.float64)   # edge (3,4) has no triangle
+    R = np.stack([np.eye(3)] * 4, axis=2)
+    inc = O.build_incidence(Ind, n_sample=None, seed=0)
+    b = OC.pgd(inc, O.cycle_inconsistency(inc, R), 3, O.ConstantStepSize(0.01))
+    assert b[0][3] == 1.0                                               # DESC.m:148
