@@ -237,7 +237,13 @@ k_pgd_stream(StreamArgs sa) {
             // Branch-free inner loop: a lane's EPL slots are idx = r + x*G; lanes past the end of the
             // slot list read harmless stage bytes and are neutralised with selects.
             const int r = threadIdx.x & (G - 1);
-            const int q = threadIdx.x / G;           // edge within the tile
+            // edge within the tile.  The groups of a warp take the warp's edges in the order even edges
+            // (first half-warp), odd edges (second half-warp): consecutive slot lists are ~max_ns doubles
+            // apart, so neighbouring edges in one half-warp collide in the shared-memory banks (for
+            // 30-slot lists: 2-way on every 64-bit stage access), edges two apart do not.
+            constexpr int GPW = 32 / G;              // groups (= edges) per warp
+            const int g = (threadIdx.x & 31) / G;
+            const int q = (threadIdx.x >> 5) * GPW + (GPW >= 4 ? 2 * (g % (GPW / 2)) + g / (GPW / 2) : g);
             const double nlr = -a.p.lr;
             int s = 0;
             uint32_t ph = 0;
