@@ -84,3 +84,14 @@ def test_config5_sfm_shaped_n50000_deg100_50_cycles_per_edge():
     corr = mo["corrupted"].cpu().numpy()
     assert S[corr].mean() > 3.0 * S[~corr].mean()
     assert info["m_cycle"] == int(np.minimum(a["codeg"].astype(np.int64), 50).sum())
+
+
+@pytest.mark.parametrize("case", [("configs[1]: n=1000 p=0.5 q=0.3 sigma=0.1", 1000, 0.5, 0.3, 0.1, 63, 30),
+                                  ("n=2000 p=0.5 (the size / n_sample regime of configs[2])", 2000, 0.5, 0.25, 0.1, 125, 12)])
+def test_dense_graphs_full_size_properties(case):
+    """longer slot lists (n_sample 63 and 125: 8 / 16 lanes per edge in the streamed kernel) at full size"""
+    _, n, p, q, sigma, ns_rule, iters = case
+    mo = synth.uniform_topology(n, p, q, sigma, "uniform", seed=3, device="cuda")
+    a = _solve(mo, n, iters, desc_b200.ConstantStepSize(0.01), 0)
+    assert abs(a["info"]["n_sample"] - ns_rule) <= 1
+    _check_properties(a, mo, a["info"]["n_sample"], 2.0)
