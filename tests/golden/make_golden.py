@@ -11,7 +11,9 @@ Models/Nonuniform_Topology.m).  PARITY UNPINNED against an execution of the real
 ``nosample`` fixture, where datasample is never called, the real reference is deterministic).
 
 Each ``.npz`` holds the inputs (Ind, RijMat, R_orig, ErrVec, params) and the literal outputs
-(incidence arrays, S0_long, wijk, S_vec, hist, iters_run, R_est of GCW).
+(incidence arrays, S0_long, wijk, S_vec, hist, iters_run, R_est of GCW) and, for the whole ``DESC()``
+call, the refinement stage DESC.m:265-312 started from them (R_laa, laa_scores; oracle.laa_refine, a
+statement-by-statement restatement of the loop and of Utils/Weighted_LAA.m).
 """
 import os
 import sys
@@ -71,6 +73,9 @@ def main():
             Ind_jk=ex["Ind_jk"], Ind_ki=ex["Ind_ki"], IJK=ex["IJK"], IKJ=ex["IKJ"], JKI=ex["JKI"],
             S0_long=ex["S0_long"], wijk=ex["wijk"], S_vec=S_vec, hist=ex["hist"], iters_run=np.int64(ex["iters_run"]),
             R_est=R_est)
+        R_laa, li = O.laa_refine(mo["Ind"], mo["RijMat"], S_vec, R_est, return_info=True)
+        out["R_laa"] = R_laa
+        out["laa_scores"] = li["scores"]
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         mat = {k: v for k, v in out.items() if k not in ("rule_kind",)}
         mat["rule_kind"] = rule_spec[0]

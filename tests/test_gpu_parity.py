@@ -51,6 +51,17 @@ def test_golden_fixture(name):
     assert ang.mean() <= ROT_TOL_DEG
 
 
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_fixture_laa_refinement(name):
+    """DESC.m:265-312 on the fixture's own (S_vec, R_est): same IRLS iterations, scores and rotations"""
+    g = load_golden(name)
+    with desc_b200.Solver(g["Ind"], g["RijMat"]) as s:
+        R, scores = s.refine(S_vec=g["S_vec"], R_init=g["R_est"])
+    assert len(scores) == len(g["laa_scores"])
+    np.testing.assert_allclose(scores, g["laa_scores"], rtol=1e-7, atol=1e-11)
+    assert O.aligned_angle_deg(R, g["R_laa"]).mean() <= ROT_TOL_DEG
+
+
 @pytest.mark.parametrize("name", ["uniform_n60_sigma0", "nonuniform_n64_adv"])
 def test_golden_fixture_explicit_cycle_lists(name):
     """the cycle lists of a reference run can be passed in (what a MATLAB datasample drew),

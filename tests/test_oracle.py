@@ -228,3 +228,11 @@ def test_c_restatement_early_stop_and_edges_without_cycles():
     inc = O.build_incidence(Ind, n_sample=None, seed=0)
     b = OC.pgd(inc, O.cycle_inconsistency(inc, R), 3, O.ConstantStepSize(0.01))
     assert b[0][3] == 1.0                                               # DESC.m:148
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_laa_reproduces_golden(name):
+    g = load_golden(name)
+    R, info = O.laa_refine(g["Ind"], g["RijMat"], g["S_vec"], g["R_est"], return_info=True)
+    np.testing.assert_allclose(info["scores"], g["laa_scores"], rtol=1e-9, atol=1e-13)
+    assert O.aligned_angle_deg(R, g["R_laa"]).mean() <= 1e-9
