@@ -759,7 +759,7 @@ static int launch_passb(desc_b200_handle* h, const BlkArgs& a, const double* w_t
 #define PB_LAUNCH(NW)                                                                                              \
     {                                                                                                              \
         CUDA_TRY(cudaFuncSetAttribute(k_pgd_passb<true, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_pgd_passb<true, NW><<<h->n, NW * 32, smem, h->stream>>>(a, w_t, h->jhdr, h->sjk);                          \
+        k_pgd_passb<true, NW><<<h->n, NW * 32, smem, h->stream>>>(a, w_t, h->jhdr, h->sjk, (h->max_ns + 31) / 32);                          \
     }
     if (nw >= 8) PB_LAUNCH(8) else if (nw >= 4) PB_LAUNCH(4) else PB_LAUNCH(2)
 #undef PB_LAUNCH

@@ -26,7 +26,10 @@
 // the O(degree) table prologue / flush of one CTA overlaps the others'.
 template <bool WRITE_SJK, int PB_WARPS>
 __global__ void __launch_bounds__(PB_WARPS * 32)
-k_pgd_passb(BlkArgs a, const double* __restrict__ w, const int2* __restrict__ jhdr, double* __restrict__ sjk) {
+k_pgd_passb(BlkArgs a, const double* __restrict__ w, const int2* __restrict__ jhdr, double* __restrict__ sjk,
+            int cpe) {
+    // cpe = ceil(longest slot list / 32): an in-edge is walked as `cpe` pieces of <= 32 slots ("virtual
+    // edges": ranks inside one edge are distinct, so its pieces never conflict with each other)
     if (a.p.ctrl[0]) return;
     constexpr int PB_TB = PB_WARPS * 32;
     extern __shared__ double sh[];
@@ -82,10 +85,24 @@ k_pgd_passb(BlkArgs a, const double* __restrict__ w, const int2* __restrict__ jh
         double w[U];
         uint32_t r[U];
     };
+    const int nv = (hi - lo) * cpe;          // virtual edges of this vertex
+    auto header = [&](int vi) {              // (first slot, slot count <= 32) of virtual edge vi
+        int2 hh = make_int2(0, 0);
+        if (vi < nv) {
+            if (cpe == 1) {
+                hh = shdr[vi];
+            } else {
+                const int r = vi / cpe, j = vi - r * cpe;
+                const int2 e = shdr[r];
+                hh = make_int2(e.x + 32 * j, max(0, min(32, e.y - 32 * j)));
+            }
+        }
+        return hh;
+    };
     auto load = [&](Buf& B, int bb) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            B.h[u] = bb + u < hi ? shdr[bb + u - lo] : make_int2(0, 0);
+            B.h[u] = header(bb + u);
             B.w[u] = 0.0;
             B.r[u] = 0u;
             if (lane < B.h[u].y) {
@@ -99,8 +116,8 @@ k_pgd_passb(BlkArgs a, const double* __restrict__ w, const int2* __restrict__ jh
     // edge u's weights and the line of its ranks.  Takes the DRAM latency off the register pipeline.
     auto prefetch = [&](int bb) {
         const int u = lane >> 2, part = lane & 3;
-        if (u < U && bb + u < hi) {
-            const int2 hh = shdr[bb + u - lo];
+        if (u < U) {
+            const int2 hh = header(bb + u);
             if (part * 16 < hh.y) {
                 const void* ptr = part < 3 ? (const void*)(w + hh.x + part * 16) : (const void*)(RK + hh.x);
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
@@ -123,35 +140,25 @@ k_pgd_passb(BlkArgs a, const double* __restrict__ w, const int2* __restrict__ jh
             TA[ia] = t + (f ? B.w[u] : 0.0);
             __syncwarp();
         }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (B.h[u].y > 32) {   // slot lists longer than a warp (ranks of one edge are distinct)
-                for (int i2 = lane + 32; i2 < B.h[u].y; i2 += 32) {
-                    const uint32_t rr = RK[B.h[u].x + i2];
-                    if (WRITE_SJK) sjk[B.h[u].x + i2] = T_S[rr & RK_MASK];
-                    if (rr & RK_APP) TA[rr & RK_MASK] += w[B.h[u].x + i2];
-                }
-                __syncwarp();
-            }
-        }
     };
     const int stride = PB_WARPS * U;
-    int base = lo + warp * U;
+    int base = warp * U;
+    const int hi_v = nv;
     Buf X, Y, Z;
     load(X, base);
     load(Y, base + stride);
     load(Z, base + 2 * stride);
 #pragma unroll
     for (int k = 3; k < 3 + PB_PF; k++) prefetch(base + k * stride);
-    while (base < hi) {
+    while (base < hi_v) {
         work(X);
         load(X, base + 3 * stride);
         prefetch(base + (3 + PB_PF) * stride);
-        if (base + stride >= hi) break;
+        if (base + stride >= hi_v) break;
         work(Y);
         load(Y, base + 4 * stride);
         prefetch(base + (4 + PB_PF) * stride);
-        if (base + 2 * stride >= hi) break;
+        if (base + 2 * stride >= hi_v) break;
         work(Z);
         load(Z, base + 5 * stride);
         prefetch(base + (5 + PB_PF) * stride);
