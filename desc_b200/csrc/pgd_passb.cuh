@@ -46,7 +46,8 @@ k_pgd_passb(BlkArgs a, const double* __restrict__ w, const int2* __restrict__ jh
     int2* shdr = reinterpret_cast<int2*>(T_acc + (size_t)PB_WARPS * a.tstride);   // headers of the in-edges [lo, hi)
     // table prologue, KU entries per thread at a time: all index loads, then all S gathers, in flight
     // together (a plain loop serialises two dependent global latencies per trip)
-    constexpr int KU = 5;
+    // (KU grows as the CTA shrinks: a 2-warp CTA - multi-GPU shards - still covers ~1280 entries per trip)
+    constexpr int KU = 40 / PB_WARPS;
     for (int rb = threadIdx.x; rb < deg; rb += PB_TB * KU) {
         int e2[KU];
         double sv[KU];
