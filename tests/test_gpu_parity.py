@@ -298,6 +298,17 @@ def test_boundary_rejects_contract_violations():
         with pytest.raises(desc_b200.DescError) as e:
             s.build_incidence(cycles=(ptr, np.full(Ind.shape[0], int(Ind[0, 0]) - 1, dtype=np.int32)))
         assert e.value.code == _lib.ERR_ARG                     # apex is not a common neighbour
+    with desc_b200.Solver(Ind, R) as s:
+        with pytest.raises(desc_b200.DescError) as e:
+            s.refine()                                          # no S_vec / R_init on the handle yet
+        assert e.value.code == _lib.ERR_STATE
+        with pytest.raises(desc_b200.DescError) as e:
+            s.refine(S_vec=np.full(Ind.shape[0], 0.1))          # S_vec given, but no rotations to start from
+        assert e.value.code == _lib.ERR_STATE
+        with pytest.raises(ValueError):
+            s.refine(S_vec=np.zeros(3), R_init=mo["R_orig"])
+        Rr, sc = s.refine(S_vec=np.full(Ind.shape[0], 0.1), R_init=mo["R_orig"])   # explicit inputs suffice
+        assert Rr.shape == mo["R_orig"].shape and len(sc) >= 1
 
 
 def test_solve_entry_point_and_device_resident_inputs():
