@@ -25,6 +25,8 @@ SYMBOLS = [
     "desc_b200_pgd", "desc_b200_gcw", "desc_b200_refine", "desc_b200_solve", "desc_b200_get_info", "desc_b200_get_codeg",
     "desc_b200_get_incidence", "desc_b200_get_slots", "desc_b200_get_s0", "desc_b200_get_w",
     "desc_b200_get_gcw_info", "desc_b200_get_timings", "desc_b200_sync",
+    "desc_b200_cemp", "desc_b200_cemp_gcw", "desc_b200_cycle_reweight", "desc_b200_rotation_alignment",
+    "desc_b200_pgd_diag",
 ]
 
 
@@ -51,10 +53,11 @@ class Timings(C.Structure):
                 ("pgd_ms", C.c_double), ("gcw_ms", C.c_double), ("d2h_ms", C.c_double), ("pgd_iter_ms", C.c_double),
                 ("pgd_launches", C.c_int32), ("gcw_iters", C.c_int32), ("total_launches", C.c_int32),
                 ("reserved", C.c_int32), ("pgd_pass1_ms", C.c_double), ("pgd_pass2_ms", C.c_double),
-                ("pgd_comm_ms", C.c_double), ("laa_ms", C.c_double), ("laa_iters", C.c_int32), ("laa_cg_iters", C.c_int32)]
+                ("pgd_comm_ms", C.c_double), ("laa_ms", C.c_double), ("laa_iters", C.c_int32), ("laa_cg_iters", C.c_int32),
+                ("cemp_ms", C.c_double), ("cemp_iters", C.c_int32), ("reserved2", C.c_int32)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
 
 
 _lib = None
@@ -94,6 +97,11 @@ def load():
     lib.desc_b200_get_gcw_info.argtypes = [vp, C.POINTER(C.c_double)]
     lib.desc_b200_get_timings.argtypes = [vp, C.POINTER(Timings)]
     lib.desc_b200_sync.argtypes = [vp]
+    lib.desc_b200_cemp.argtypes = [vp, i32, dp, i32, dp]
+    lib.desc_b200_cemp_gcw.argtypes = [vp, dp, dp]
+    lib.desc_b200_cycle_reweight.argtypes = [vp, dp, C.c_double, C.c_double, dp]
+    lib.desc_b200_rotation_alignment.argtypes = [vp, dp, dp, dp, dp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.desc_b200_pgd_diag.argtypes = [vp, i32, C.POINTER(StepRule), dp, dp, dp, dp, dp, C.POINTER(i32)]
     _lib = lib
     return lib
 

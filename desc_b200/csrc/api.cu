@@ -71,7 +71,8 @@ void desc_b200_destroy(desc_b200_handle* h) {
                     h->S[0], h->S[1], h->acc[0], h->acc[1], h->adam_m, h->adam_v, h->d_hist, h->d_ctrl,
                     h->d_ctrl_f, h->omega, h->isd, h->X[0], h->X[1], h->gcw_coef, h->gcw_red,
                     h->gcw_small, h->gcw_res, h->R_est, h->d_err, h->d_Sin, h->rk_i, h->rk_j, h->estart,
-                    h->pgd_partial, h->jhdr, h->sjk, h->thr_key, h->thr_k, h->comm_scratch};
+                    h->pgd_partial, h->jhdr, h->sjk, h->thr_key, h->thr_k, h->comm_scratch,
+                    h->cemp_S[0], h->cemp_S[1], h->diag_work, h->diag_hist};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
@@ -312,6 +313,150 @@ int desc_b200_solve(desc_b200_handle* h, int32_t n_sample, uint64_t seed, int32_
         h->tm.d2h_ms += d2h;
     }
     return DESC_B200_OK;
+}
+
+// ---- CEMP / CEMP+GCW on the same incidence ---------------------------------
+int desc_b200_cemp(desc_b200_handle* h, int32_t max_iter, const double* reweighting, int32_t n_reweighting,
+                   double* SVec_out) {
+    DESC_TRY(check_handle(h));
+    {
+        StageTimer t(h, &h->tm.cemp_ms);
+        DESC_TRY(desc_cemp_impl(h, max_iter, reweighting, n_reweighting));
+        DESC_TRY(t.stop());
+    }
+    h->tm.cemp_iters = max_iter;
+    if (SVec_out) {
+        CUDA_TRY(cudaMemcpyAsync(SVec_out, h->cemp_S[h->cemp_final], h->m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    h->tm.total_launches = h->launches;
+    return DESC_B200_OK;
+}
+
+int desc_b200_cemp_gcw(desc_b200_handle* h, const double* SVec, double* R_out) {
+    DESC_TRY(check_handle(h));
+    const double* d_S = nullptr;
+    if (SVec) {
+        if (!h->d_Sin) CUDA_TRY(cudaMalloc(&h->d_Sin, h->m * sizeof(double)));
+        CUDA_TRY(cudaMemcpyAsync(h->d_Sin, SVec, h->m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        d_S = h->d_Sin;
+    } else {
+        if (!h->have_cemp) {
+            desc_set_error("cemp_gcw with SVec=NULL needs a previous cemp on this handle");
+            return DESC_B200_ERR_STATE;
+        }
+        d_S = h->cemp_S[h->cemp_final];
+    }
+    int rc;
+    {
+        StageTimer t(h, &h->tm.gcw_ms);
+        h->gcw_weight_rule = 1;   // CEMP_GCW.m:141
+        rc = desc_gcw_impl(h, d_S);
+        h->gcw_weight_rule = 0;
+        if (rc == DESC_B200_OK) rc = t.stop();
+    }
+    DESC_TRY(rc);
+    h->have_gcw = true;
+    if (R_out) {
+        CUDA_TRY(cudaMemcpyAsync(R_out, h->R_est, 9 * (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    h->tm.total_launches = h->launches;
+    return DESC_B200_OK;
+}
+
+int desc_b200_cycle_reweight(desc_b200_handle* h, const double* x, double beta, double empty_value, double* out) {
+    DESC_TRY(check_handle(h));
+    if (!h->have_s0) {
+        desc_set_error("cycle_reweight before cycle_inconsistency");
+        return DESC_B200_ERR_STATE;
+    }
+    if (!x || !out) {
+        desc_set_error("cycle_reweight: null vector");
+        return DESC_B200_ERR_ARG;
+    }
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (size_t)2 * h->m * sizeof(double)));
+    int rc = DESC_B200_OK;
+    cudaError_t e = cudaMemcpyAsync(d, x, h->m * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) rc = desc_cemp_reweight(h, d, d + h->m, beta, empty_value);
+    if (e == cudaSuccess && rc == DESC_B200_OK)
+        e = cudaMemcpyAsync(out, d + h->m, h->m * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        desc_set_error("CUDA error %s in cycle_reweight", cudaGetErrorString(e));
+        return DESC_B200_ERR_CUDA;
+    }
+    h->tm.total_launches = h->launches;
+    return rc;
+}
+
+// ---- evaluation / diagnostics -----------------------------------------------
+int desc_b200_rotation_alignment(desc_b200_handle* h, const double* R_est, const double* R_gt, double* R_out,
+                                 double* R_align, double* mean_error, double* median_error) {
+    DESC_TRY(check_handle(h));
+    if (!R_est || !R_gt) {
+        desc_set_error("rotation_alignment: null rotations");
+        return DESC_B200_ERR_ARG;
+    }
+    const size_t n9 = 9 * (size_t)h->n;
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 3 * n9 * sizeof(double)));
+    double a[11];
+    int rc = DESC_B200_OK;
+    cudaError_t e = cudaMemcpyAsync(d, R_est, n9 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n9, R_gt, n9 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) rc = desc_align_impl(h, d, d + n9, d + 2 * n9, a);
+    if (e == cudaSuccess && rc == DESC_B200_OK && R_out)
+        e = cudaMemcpyAsync(R_out, d + 2 * n9, n9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        desc_set_error("CUDA error %s in rotation_alignment", cudaGetErrorString(e));
+        return DESC_B200_ERR_CUDA;
+    }
+    DESC_TRY(rc);
+    if (mean_error) *mean_error = a[0];
+    if (median_error) *median_error = a[1];
+    if (R_align) memcpy(R_align, a + 2, 9 * sizeof(double));
+    h->tm.total_launches = h->launches;
+    return DESC_B200_OK;
+}
+
+int desc_b200_pgd_diag(desc_b200_handle* h, int32_t iters, desc_b200_step_rule* rule, const double* ErrVec,
+                       const double* R_orig, double* S_vec_out, double* hist_out, double* diag_out,
+                       int32_t* iters_run_out) {
+    DESC_TRY(check_handle(h));
+    if (!ErrVec || !R_orig || !diag_out || iters < 0) {
+        desc_set_error("pgd_diag needs ErrVec (m), R_orig (3x3xn) and diag_out (3*iters)");
+        return DESC_B200_ERR_ARG;
+    }
+    const size_t n9 = 9 * (size_t)h->n;
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, ((size_t)h->m + n9) * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d, ErrVec, h->m * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + h->m, R_orig, n9 * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        desc_set_error("CUDA error %s in pgd_diag", cudaGetErrorString(e));
+        return DESC_B200_ERR_CUDA;
+    }
+    for (int t = 0; t < 3 * iters; t++) diag_out[t] = 0.0;
+    h->diag_on = true;
+    h->diag_err = d;
+    h->diag_Rgt = d + h->m;
+    h->diag_out = diag_out;
+    h->diag_cap = iters;
+    const int rc = desc_b200_pgd(h, iters, rule, S_vec_out, hist_out, iters_run_out);
+    h->diag_on = false;
+    h->diag_err = h->diag_Rgt = nullptr;
+    h->diag_out = nullptr;
+    h->diag_cap = 0;
+    cudaFree(d);
+    if (rc == DESC_B200_OK && iters_run_out)
+        for (int t = 3 * *iters_run_out; t < 3 * iters; t++) diag_out[t] = 0.0;
+    return rc;
 }
 
 // ---- getters ---------------------------------------------------------------------------

@@ -704,7 +704,7 @@ static void free_incidence(desc_b200_handle* h) {
     h->pk_jk = h->pk_ki = nullptr;
     h->S0 = nullptr;
     h->adam_m = h->adam_v = nullptr;
-    h->built = h->have_s0 = h->have_pgd = false;
+    h->built = h->have_s0 = h->have_pgd = h->have_cemp = false;
 }
 
 int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t seed,

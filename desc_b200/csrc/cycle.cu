@@ -17,20 +17,7 @@
 // edge's slots; R_ij is loaded once per lane (broadcast within the group), R_jk / R_ki are the
 // two gathers.  HBM-bound; tensor cores deliberately unused (3x3 gather arithmetic).
 #include "internal.cuh"
-
-__device__ __forceinline__ double abs_acos_dev(double x) {
-    if (x > 1.0) {
-        double t = x - 1.0;
-        return log1p(t + sqrt(t * (t + 2.0)));
-    }
-    if (x < -1.0) {
-        double t = -x - 1.0;
-        double a = log1p(t + sqrt(t * (t + 2.0)));
-        const double pi = 3.14159265358979323846;
-        return sqrt(pi * pi + a * a);
-    }
-    return acos(x);
-}
+#include "so3.cuh"
 
 // M(r,c) of a stored column-major 3x3, optionally transposed
 #define MAT(p, r, c, tr) ((tr) ? (p)[(c) + 3 * (r)] : (p)[(r) + 3 * (c)])

@@ -146,6 +146,21 @@ struct desc_b200_handle {
     double* d_Sin = nullptr;    // m: S_vec passed to gcw from the host
     bool have_gcw = false;
     int laa_cg_iters = 0;       // CG iterations of the last refine call
+    int gcw_weight_rule = 0;    // 0: GCW.m:20 (s^1.5), 1: CEMP_GCW.m:141 (s)
+
+    // CEMP (cemp.cu) --------------------------------------------------------------------
+    double* cemp_S[2] = {nullptr, nullptr};  // m each (ping-pong)
+    int cemp_final = 0;
+    bool have_cemp = false;
+
+    // make_plots diagnostics (diag.cu): per-iteration S_vec error, GCW, alignment (DESC.m:235-239)
+    bool diag_on = false;
+    const double* diag_err = nullptr;   // ErrVec on the device (m)
+    const double* diag_Rgt = nullptr;   // R_orig on the device (9n)
+    double* diag_out = nullptr;         // host, 3 per iteration
+    int diag_cap = 0;
+    double* diag_work = nullptr;        // device scratch of the alignment
+    unsigned* diag_hist = nullptr;      // radix-select histogram
 
     // scratch ---------------------------------------------------------------------------
     int* d_err = nullptr;       // device error flags
@@ -162,6 +177,15 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
 int desc_gcw_impl(desc_b200_handle* h, const double* d_S);
 int desc_laa_impl(desc_b200_handle* h, const double* d_S, const double* d_Rinit, double* d_Rout, int max_iters,
                   double stop_threshold, int* iters_run, double* scores_host);
+int desc_cemp_impl(desc_b200_handle* h, int max_iter, const double* beta, int n_beta);
+int desc_cemp_reweight(desc_b200_handle* h, const double* x_cur, double* x_next, double beta, double empty_value);
+// Rotation_Alignment.m on the device: out[0]=mean error, out[1]=median error (degrees), out[2..10]=R_align;
+// d_Rout (may be null) receives R_est*R_align
+int desc_align_impl(desc_b200_handle* h, const double* d_Rest, const double* d_Rgt, double* d_Rout, double out[11]);
+// called by the PGD loop after iteration t when h->diag_on (DESC.m:235-239)
+int desc_diag_record(desc_b200_handle* h, int t, const double* d_S);
+// k-th smallest (1-based) of non-negative doubles on the device (laa.cu); d_hist: 2048 unsigned
+int desc_select_kth(desc_b200_handle* h, const double* X, int64_t m, int64_t k, unsigned* d_hist, double* out);
 int desc_exclusive_scan_i64(desc_b200_handle* h, const int* in, int64_t* out, int64_t count);
 
 // multi-GPU collectives (comm.cu); no-ops when world==1

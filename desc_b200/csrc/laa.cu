@@ -388,6 +388,10 @@ int laa_select(desc_b200_handle* h, const double* X, int64_t m, int64_t k, unsig
 }
 }  // namespace
 
+int desc_select_kth(desc_b200_handle* h, const double* X, int64_t m, int64_t k, unsigned* d_hist, double* out) {
+    return laa_select(h, X, m, k, d_hist, out);
+}
+
 // MATLAB quantile(x, p) of a device vector of non-negative doubles (DESC.m:276,301)
 static int laa_quantile(desc_b200_handle* h, const double* X, int64_t m, double p, unsigned* d_hist, double* out) {
     const double pos = (double)m * p + 0.5;

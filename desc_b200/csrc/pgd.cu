@@ -938,7 +938,7 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
     }
     int t_done = 0;
     bool stopped = false;
-    const int check_every = 8;
+    const int check_every = h->diag_on ? 1 : 8;   // diagnostics run a GCW per iteration: stop as soon as the rule says
     for (int t = 1; t <= iters && !stopped; t++) {
         const int cur = (t - 1) & 1, nxt = t & 1;
         // the streamed kernel stores every partner-sum entry of its vertex range (no zero-fill needed
@@ -993,6 +993,7 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
             if (!stream) DESC_TRY(desc_allgather_ranges(h, h->S[nxt], sizeof(double), h->shard_edges));
         }
         if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 4], st));
+        if (h->diag_on) DESC_TRY(desc_diag_record(h, t, h->S[nxt]));   // make_plots branch, DESC.m:235-239
         k_pgd_finalize<<<1, 1, 0, st>>>(h->acc[nxt] + 2 * m, t, 0, m, 1e-5, 30, h->d_hist, h->d_ctrl, h->d_ctrl_f);
         KERNEL_CHECK(h);
         t_done = t;

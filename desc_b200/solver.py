@@ -8,12 +8,18 @@ Function names, argument meaning and outputs follow the reference's MATLAB funct
 * ``GCW(Ind, AdjMat, RijMat, S_vec) -> R_est``            Utils/GCW.m:1
 * step rules ``ConstantStepSize``, ``PiecewiseStepSize``, ``HybridGradient``  (Utils/*.m)
 
+* ``CEMP(Ind, RijMat, CEMP_parameters) -> SVec``          Algorithms/CEMP.m:25      
+* ``CEMP_GCW(Ind, RijMat, CEMP_parameters) -> R_est``     Algorithms/CEMP_GCW.m:25
+* ``Rotation_Alignment(R_est, R_gt) -> (R_out, R_align, mean_error, median_error)``  Utils/Rotation_Alignment.m:13
+
 ``Ind`` is the reference's m x 2, 1-based, i<j, (i,j)-sorted edge list; ``RijMat`` is
 3 x 3 x m; ``params`` is a dict with the reference's field names (``iters``, ``Gradient``,
 ``make_plots``, ``ErrVec``, ``R_orig``; ``learning_rate`` is accepted and ignored exactly as
 in DESC.m:169).  Extra, optional keys that the reference cannot express: ``n_sample``
 (0 = reference rule), ``seed`` (sampler seed), ``cycles`` (explicit ``(ptr, apex)`` lists),
-``verbose`` (print the reference's per-iteration progress line, DESC.m:241).
+``verbose`` (print the reference's per-iteration progress line, DESC.m:241).  ``make_plots=True``
+(DESC.m:235-239) needs ``ErrVec`` and ``R_orig``; the four convergence curves are computed on the device and
+left in ``desc_b200.solver.last_diagnostics`` (and drawn like DESC.m:315-344 when matplotlib is importable).
 
 All arithmetic happens on the GPU inside ``libdesc_b200.so``.  Nothing here computes.
 """
@@ -222,6 +228,68 @@ class Solver:
         _lib.check(self._lib.desc_b200_refine(self._h, _ptr(S), _ptr(R0), _ptr(R), C.byref(run), _ptr(scores)))
         return R, scores[:run.value].copy()
 
+    # -- CEMP on the same incidence, evaluation, diagnostics -----------
+    def cemp(self, max_iter, reweighting):
+        """CEMP.m:98-129 on the handle's incidence (after build_incidence + cycle_inconsistency) -> SVec (m,)."""
+        beta = np.ascontiguousarray(np.asarray(reweighting, dtype=np.float64).ravel())
+        if int(max_iter) > 0 and beta.size == 0:
+            raise ValueError("reweighting must not be empty")
+        S = np.empty(self.m, dtype=np.float64)
+        _lib.check(self._lib.desc_b200_cemp(self._h, int(max_iter), _ptr(beta), int(beta.size), _ptr(S)))
+        return S
+
+    def cemp_gcw(self, SVec=None):
+        """CEMP_GCW.m:127-159 -> R_est 3x3xn (SVec default: the last cemp on this handle)."""
+        S = None if SVec is None else np.ascontiguousarray(np.asarray(SVec, dtype=np.float64).ravel())
+        if S is not None and S.size != self.m:
+            raise ValueError("SVec must have m entries")
+        R = np.empty((3, 3, self.info()["n"]), dtype=np.float64, order="F")
+        _lib.check(self._lib.desc_b200_cemp_gcw(self._h, _ptr(S), _ptr(R)))
+        return R
+
+    def cycle_reweight(self, x, beta, empty_value=1.0):
+        """One cycle reweighting of an edge vector (CEMP.m:109-125; HVec of MPLS.m:219-233)."""
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel())
+        if x.size != self.m:
+            raise ValueError("x must have m entries")
+        out = np.empty(self.m, dtype=np.float64)
+        _lib.check(self._lib.desc_b200_cycle_reweight(self._h, _ptr(x), float(beta), float(empty_value), _ptr(out)))
+        return out
+
+    def rotation_alignment(self, R_est, R_gt):
+        """Utils/Rotation_Alignment.m:13-38 -> (R_out, R_align, mean_error, median_error)."""
+        n = self.info()["n"]
+        Re = np.asfortranarray(np.asarray(R_est, dtype=np.float64))
+        Rg = np.asfortranarray(np.asarray(R_gt, dtype=np.float64))
+        if Re.shape != (3, 3, n) or Rg.shape != (3, 3, n):
+            raise ValueError("R_est and R_gt must be 3 x 3 x n")
+        R_out = np.empty((3, 3, n), dtype=np.float64, order="F")
+        R_align = np.empty((3, 3), dtype=np.float64, order="F")
+        mean, med = C.c_double(0.0), C.c_double(0.0)
+        _lib.check(self._lib.desc_b200_rotation_alignment(self._h, _ptr(Re), _ptr(Rg), _ptr(R_out), _ptr(R_align),
+                                                         C.byref(mean), C.byref(med)))
+        return R_out, R_align, float(mean.value), float(med.value)
+
+    def pgd_diag(self, iters, rule, ErrVec, R_orig):
+        """pgd with the make_plots branch (DESC.m:235-239) -> (S_vec, hist, iters_run, diag) where diag[t] =
+        [mean(abs(ErrVec-S_vec)), MSE_mean, MSE_median] after iteration t+1."""
+        iters = int(iters)
+        n = self.info()["n"]
+        Err = np.ascontiguousarray(np.asarray(ErrVec, dtype=np.float64).ravel())
+        Ro = np.asfortranarray(np.asarray(R_orig, dtype=np.float64))
+        if Err.size != self.m or Ro.shape != (3, 3, n):
+            raise ValueError("ErrVec must have m entries and R_orig must be 3 x 3 x n")
+        S = np.empty(self.m, dtype=np.float64)
+        hist = np.zeros((max(iters, 1), 2), dtype=np.float64)
+        diag = np.zeros((max(iters, 1), 3), dtype=np.float64)
+        r = rule._to_c()
+        run = C.c_int32(0)
+        _lib.check(self._lib.desc_b200_pgd_diag(self._h, iters, C.byref(r), _ptr(Err), _ptr(Ro), _ptr(S), _ptr(hist),
+                                               _ptr(diag), C.byref(run)))
+        rule._from_c(r)
+        k = int(run.value)
+        return S, hist[:k], k, diag[:k]
+
     # -- getters -------------------------------------------------------------------------
     def info(self):
         a = (C.c_int64 * 10)()
@@ -297,13 +365,57 @@ def _param(params, key, default=None):
     return getattr(params, key, default)
 
 
-def _run_pgd(Ind, RijMat, params, want_gcw, **solver_kw):
+#: convergence curves of the last solve run with ``make_plots=True`` (DESC.m:174-178,235-239)
+last_diagnostics = None
+
+
+def _check_params(params):
     rule = _param(params, "Gradient")
     if rule is None or not hasattr(rule, "_to_c"):
         raise ValueError("params.Gradient must be a ConstantStepSize / PiecewiseStepSize / HybridGradient object")
-    if _param(params, "make_plots", False):
-        raise NotImplementedError("params.make_plots=true (per-iteration GCW diagnostics and figures, "
-                                  "DESC.m:235-239,315-344) is not part of the device hot path")
+    if _param(params, "make_plots", False) and (_param(params, "ErrVec") is None or _param(params, "R_orig") is None):
+        raise ValueError("params.make_plots=true needs params.ErrVec and params.R_orig (DESC.m:236-238)")
+    return rule
+
+
+def _pgd_stage(s, params, rule):
+    """DESC.m:164-261 on solver ``s``; with make_plots the diagnostics branch runs on the device as well."""
+    global last_diagnostics
+    iters = int(_param(params, "iters"))
+    if not _param(params, "make_plots", False):
+        return s.pgd(iters, rule)
+    ErrVec, R_orig = _param(params, "ErrVec"), _param(params, "R_orig")
+    S_vec, hist, iters_run, diag = s.pgd_diag(iters, rule, ErrVec, R_orig)
+    last_diagnostics = dict(svec_errors=diag[:, 0].copy(), obj_vals=hist[:, 1].copy(), MSE_means=diag[:, 1].copy(),
+                            MSE_medians=diag[:, 2].copy())
+    _draw_plots(last_diagnostics)
+    return S_vec, hist, iters_run
+
+
+def _draw_plots(d):
+    """DESC.m:315-344: the 2x2 figure.  Only if matplotlib is installed; the curves are in last_diagnostics."""
+    try:
+        import matplotlib.pyplot as plt
+    except Exception:
+        return
+    fig, ax = plt.subplots(2, 2)
+    for a, key, title, yl in ((ax[0, 0], "svec_errors", "Convergence of Corruption Estimate Vector (S_vec, sampled)",
+                               "Average distance to true corruption"),
+                              (ax[0, 1], "obj_vals", "Convergence of Objective Function (sampled)",
+                               "Value of Objective Function"),
+                              (ax[1, 0], "MSE_means", "Convergence of Rotation Estimate, Mean (sampled)",
+                               "Mean Error in R estimate (degrees)"),
+                              (ax[1, 1], "MSE_medians", "Convergence of Rotation Estimate, Median (sampled)",
+                               "Median Error in R estimate (degrees)")):
+        a.plot(d[key])
+        a.set_title(title)
+        a.set_xlabel("Iteration number")
+        a.set_ylabel(yl)
+    d["figure"] = fig
+
+
+def _run_pgd(Ind, RijMat, params, want_gcw, **solver_kw):
+    rule = _check_params(params)
     iters = int(_param(params, "iters"))
     s = Solver(Ind, RijMat, **solver_kw)
     try:
@@ -313,7 +425,7 @@ def _run_pgd(Ind, RijMat, params, want_gcw, **solver_kw):
         if _param(params, "verbose", False):
             print("Initialization completed!")              # DESC.m:160
             print("Reweighting Procedure Started ...")      # DESC.m:162
-        S_vec, hist, iters_run = s.pgd(iters, rule)
+        S_vec, hist, iters_run = _pgd_stage(s, params, rule)
         if _param(params, "verbose", False):
             for t in range(iters_run):                       # DESC.m:241
                 print("iter %d: average change in S_vec %f, objective value: %f" % (t + 1, hist[t, 0], hist[t, 1]))
@@ -339,19 +451,14 @@ def DESC_init(Ind, RijMat, params, **solver_kw):
 def DESC(Ind, RijMat, params, **solver_kw):
     """``[R_est, R_init, S_vec] = DESC(Ind, RijMat, params)`` (Algorithms/DESC.m:14): the hot path
     (DESC.m:14-263) followed by the weighted Lie-algebraic refinement (DESC.m:265-312), all on the device."""
-    rule = _param(params, "Gradient")
-    if rule is None or not hasattr(rule, "_to_c"):
-        raise ValueError("params.Gradient must be a ConstantStepSize / PiecewiseStepSize / HybridGradient object")
-    if _param(params, "make_plots", False):
-        raise NotImplementedError("params.make_plots=true (per-iteration GCW diagnostics and figures, "
-                                  "DESC.m:235-239,315-344) is not part of the device hot path")
+    rule = _check_params(params)
     verbose = _param(params, "verbose", False)
     s = Solver(Ind, RijMat, **solver_kw)
     try:
         s.build_incidence(n_sample=int(_param(params, "n_sample", 0) or 0), seed=int(_param(params, "seed", 0) or 0),
                           cycles=_param(params, "cycles"))
         s.cycle_inconsistency()
-        S_vec, hist, iters_run = s.pgd(int(_param(params, "iters")), rule)
+        S_vec, hist, iters_run = _pgd_stage(s, params, rule)
         R_init = s.gcw()
         if verbose:
             print("Rotation Initialized!")                   # DESC.m:283
@@ -372,5 +479,53 @@ def GCW(Ind, AdjMat, RijMat, S_vec, **solver_kw):
     s = Solver(Ind, RijMat, **solver_kw)
     try:
         return s.gcw(S_vec)
+    finally:
+        s.close()
+
+
+# ---------------------------------------------------------------------------------------
+# the comparators on the same incidence, and the evaluation metric
+# ---------------------------------------------------------------------------------------
+def _run_cemp(Ind, RijMat, CEMP_parameters, want_gcw, **solver_kw):
+    nsample = int(_param(CEMP_parameters, "nsample"))
+    s = Solver(Ind, RijMat, **solver_kw)
+    try:
+        s.build_incidence(n_sample=nsample, seed=int(_param(CEMP_parameters, "seed", 0) or 0),
+                          cycles=_param(CEMP_parameters, "cycles"))
+        s.cycle_inconsistency()
+        SVec = s.cemp(int(_param(CEMP_parameters, "max_iter")), _param(CEMP_parameters, "reweighting"))
+        R = s.cemp_gcw() if want_gcw else None
+    finally:
+        s.close()
+    return SVec.reshape(1, -1), R
+
+
+def CEMP(Ind, RijMat, CEMP_parameters, **solver_kw):
+    """``SVec = CEMP(Ind, RijMat, CEMP_parameters)`` (Algorithms/CEMP.m:25), SVec is 1 x m.
+
+    ``CEMP_parameters``: ``max_iter``, ``reweighting``, ``nsample`` as in the reference (``gcw_beta`` is unused there
+    too); optional ``seed`` / ``cycles`` as for DESC.  The reference samples WITH replacement (CEMP.m:63); the
+    device sampler keeps ``nsample`` distinct common neighbours (all of them when there are fewer) -- pass
+    ``cycles=(ptr, apex)`` with repeated apices to replay a MATLAB draw exactly."""
+    return _run_cemp(Ind, RijMat, CEMP_parameters, False, **solver_kw)[0]
+
+
+def CEMP_GCW(Ind, RijMat, CEMP_parameters, **solver_kw):
+    """``R_est = CEMP_GCW(Ind, RijMat, CEMP_parameters)`` (Algorithms/CEMP_GCW.m:25)."""
+    return _run_cemp(Ind, RijMat, CEMP_parameters, True, **solver_kw)[1]
+
+
+def Rotation_Alignment(R_est, R_gt, **solver_kw):
+    """``[R_out, R_align, mean_error, median_error] = Rotation_Alignment(R_est, R_gt)``
+    (Utils/Rotation_Alignment.m:13).  Needs no graph: a two-node dummy handle carries the device context."""
+    R_est = np.asarray(R_est, dtype=np.float64)
+    n = R_est.shape[2]
+    if n < 2:
+        raise ValueError("need at least two rotations")
+    Ind = np.stack([np.arange(1, n), np.arange(2, n + 1)], axis=1).astype(np.float64)   # a path: every node has an edge
+    Rij = np.tile(np.eye(3)[:, :, None], (1, 1, n - 1))
+    s = Solver(Ind, Rij, **solver_kw)
+    try:
+        return s.rotation_alignment(R_est, R_gt)
     finally:
         s.close()

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define DESC_B200_VERSION 100
+#define DESC_B200_VERSION 101
 
 #define DESC_B200_OK 0
 #define DESC_B200_ERR_ARG -1      /* bad argument / input violates the layout contract */
@@ -100,6 +100,9 @@ typedef struct desc_b200_timings {
     double laa_ms;        /* refine: all IRLS iterations                                      */
     int32_t laa_iters;    /* IRLS iterations of the last refine call                          */
     int32_t laa_cg_iters; /* CG iterations (all IRLS iterations together) of the last refine  */
+    double cemp_ms;       /* cemp: initial mean + all reweighting iterations                  */
+    int32_t cemp_iters;   /* reweighting iterations of the last cemp call                     */
+    int32_t reserved2;
 } desc_b200_timings;
 
 const char* desc_b200_last_error(void);
@@ -179,6 +182,35 @@ int desc_b200_get_gcw_info(desc_b200_handle* h, double info[8]);
    Stops like the reference: score <= 1e-3 or 99 iterations (DESC.m:272,287).  One GPU only. */
 int desc_b200_refine(desc_b200_handle* h, const double* S_vec, const double* R_init, double* R_out,
                      int32_t* iters_run, double* scores);
+
+/* ---- the comparators that share DESC's incidence ----
+   CEMP (Algorithms/CEMP.m:25-131): call after build_incidence (n_sample = CEMP_parameters.nsample, or
+   explicit cycle lists -- which may repeat an apex, as the reference's with-replacement draw CEMP.m:63
+   does) and cycle_inconsistency.  SVec_0 = mean of the edge's d_ijk (:101), then max_iter reweightings
+   SVec(l) = sum_s w_s d_s / sum_s w_s, w_s = exp(-beta_t (SVec(e_ki)+SVec(e_jk))) (:106-126); edges
+   without a 3-cycle keep 1 (:102,125).  reweighting: n_reweighting values beta_t, padded with the last
+   one as CEMP.m:31-35 does.  SVec_out: m doubles (may be NULL).                                      */
+int desc_b200_cemp(desc_b200_handle* h, int32_t max_iter, const double* reweighting, int32_t n_reweighting,
+                   double* SVec_out);
+/* CEMP_GCW.m:127-159: GCW with the weights 1./(SVec+1e-8) (:141).  SVec = NULL: the last cemp.       */
+int desc_b200_cemp_gcw(desc_b200_handle* h, const double* SVec, double* R_out);
+/* One cycle reweighting of an arbitrary edge vector x (m doubles): out(l) = sum_s w_s d_s / sum_s w_s,
+   w_s = exp(-beta (x(e_ki)+x(e_jk))); edges without cycles get empty_value.  This is CEMP.m:109-125
+   (empty_value 1) and the HVec step of MPLS.m:219-233 with x = ResVec.                                */
+int desc_b200_cycle_reweight(desc_b200_handle* h, const double* x, double beta, double empty_value, double* out);
+
+/* ---- evaluation / diagnostics ----
+   Utils/Rotation_Alignment.m:13-38 (== GlobalSOdCorrectRight.m): R_est, R_gt 3x3xn (n of the handle);
+   R_out = R_est*R_align (9n, may be NULL), R_align 9 doubles (may be NULL), errors in degrees.        */
+int desc_b200_rotation_alignment(desc_b200_handle* h, const double* R_est, const double* R_gt, double* R_out,
+                                 double* R_align, double* mean_error, double* median_error);
+/* desc_b200_pgd with params.make_plots = true (DESC.m:235-239): additionally, after every iteration t,
+   diag_out[3(t-1)..] = { mean(abs(ErrVec - S_vec)), MSE_mean, MSE_median } where the last two come from
+   GCW(S_vec) aligned to R_orig.  ErrVec: m doubles, R_orig: 3x3xn, diag_out: 3*iters doubles (rows past
+   iters_run are zero).  The figures themselves (DESC.m:315-344) are the caller's business.             */
+int desc_b200_pgd_diag(desc_b200_handle* h, int32_t iters, desc_b200_step_rule* rule, const double* ErrVec,
+                       const double* R_orig, double* S_vec_out, double* hist_out, double* diag_out,
+                       int32_t* iters_run_out);
 int desc_b200_get_timings(desc_b200_handle* h, desc_b200_timings* t);
 /* synchronise the handle's stream (for callers timing from outside) */
 int desc_b200_sync(desc_b200_handle* h);

@@ -2,6 +2,13 @@
  * desc_b200_mex.c -- thin MEX gateway: MATLAB host code -> C ABI (include/desc_b200.h) -> CUDA.
  *
  *   out = desc_b200_mex('solve', Ind, RijMat, iters, rule, n_sample, seed, want_R)
+ *   out = desc_b200_mex('solve', Ind, RijMat, iters, rule, n_sample, seed, want_R, ErrVec, R_orig)
+ *         (params.make_plots = true, DESC.m:235-239: adds out.diag = iters_run x 3
+ *          [svec_errors, MSE_means, MSE_medians])
+ *   out = desc_b200_mex('cemp',  Ind, RijMat, max_iter, reweighting, nsample, seed, want_R)
+ *         (Algorithms/CEMP.m / CEMP_GCW.m: out.SVec 1 x m, out.R_est)
+ *   out = desc_b200_mex('align', R_est, R_gt)   (Utils/Rotation_Alignment.m: out.R_out, out.R_align,
+ *          out.mean_error, out.median_error)
  *   R   = desc_b200_mex('gcw',   Ind, RijMat, S_vec)
  *   out = desc_b200_mex('refine', Ind, RijMat, S_vec, R_init)    (DESC.m:265-312; out.R_est, out.scores)
  *   n   = desc_b200_mex('device_count')
@@ -59,7 +66,8 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         return;
     }
     if (strcmp(cmd, "solve") == 0) {
-        if (nrhs != 8) mexErrMsgIdAndTxt("DESC:b200", "solve: 7 arguments expected");
+        if (nrhs != 8 && nrhs != 10) mexErrMsgIdAndTxt("DESC:b200", "solve: 7 or 9 arguments expected");
+        const int diag = nrhs == 10;
         mwSize m;
         check_inputs(prhs[1], prhs[2], &m);
         const int iters = (int)mxGetScalar(prhs[3]);
@@ -94,8 +102,23 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
             R = mxCreateDoubleMatrix(0, 0, mxREAL);
         }
         int32_t iters_run = 0;
-        fail_if(desc_b200_solve(h, n_sample, seed, iters, &rule, mxGetPr(S), want_R ? mxGetPr(R) : NULL,
-                                mxGetPr(hist), &iters_run), h);
+        mxArray* dg = NULL;
+        if (!diag) {
+            fail_if(desc_b200_solve(h, n_sample, seed, iters, &rule, mxGetPr(S), want_R ? mxGetPr(R) : NULL,
+                                    mxGetPr(hist), &iters_run), h);
+        } else {   /* params.make_plots: the diagnostics branch DESC.m:235-239 runs on the device too */
+            if (!mxIsDouble(prhs[8]) || mxGetNumberOfElements(prhs[8]) != m || !mxIsDouble(prhs[9]) ||
+                mxGetNumberOfElements(prhs[9]) != 9 * n) {
+                desc_b200_destroy(h);
+                mexErrMsgIdAndTxt("DESC:b200", "make_plots: params.ErrVec must have m entries and params.R_orig must be 3 x 3 x n");
+            }
+            dg = mxCreateDoubleMatrix(3, iters > 0 ? iters : 1, mxREAL);
+            fail_if(desc_b200_build_incidence(h, n_sample, seed, NULL, NULL), h);
+            fail_if(desc_b200_cycle_inconsistency(h), h);
+            fail_if(desc_b200_pgd_diag(h, iters, &rule, mxGetPr(prhs[8]), mxGetPr(prhs[9]), mxGetPr(S), mxGetPr(hist),
+                                       mxGetPr(dg), &iters_run), h);
+            if (want_R) fail_if(desc_b200_gcw(h, NULL, mxGetPr(R)), h);
+        }
         fail_if(desc_b200_get_info(h, info), h);
         desc_b200_destroy(h);
 
@@ -106,8 +129,15 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
             mxGetPr(histT)[t + iters_run] = mxGetPr(hist)[2 * t + 1];
         }
         mxDestroyArray(hist);
-        const char* fields[] = {"S_vec", "R_est", "hist", "iters_run", "t", "n_sample", "m_cycle"};
-        plhs[0] = mxCreateStructMatrix(1, 1, 7, fields);
+        mxArray* dgT = mxCreateDoubleMatrix(dg ? iters_run : 0, 3, mxREAL);
+        if (dg) {
+            for (int t = 0; t < iters_run; t++)
+                for (int c = 0; c < 3; c++) mxGetPr(dgT)[t + c * iters_run] = mxGetPr(dg)[3 * t + c];
+            mxDestroyArray(dg);
+        }
+        const char* fields[] = {"S_vec", "R_est", "hist", "iters_run", "t", "n_sample", "m_cycle", "diag"};
+        plhs[0] = mxCreateStructMatrix(1, 1, 8, fields);
+        mxSetField(plhs[0], 0, "diag", dgT);
         mxSetField(plhs[0], 0, "S_vec", S);
         mxSetField(plhs[0], 0, "R_est", R);
         mxSetField(plhs[0], 0, "hist", histT);
@@ -162,6 +192,76 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         plhs[0] = mxCreateStructMatrix(1, 1, 2, fields);
         mxSetField(plhs[0], 0, "R_est", R);
         mxSetField(plhs[0], 0, "scores", scores);
+        return;
+    }
+    if (strcmp(cmd, "cemp") == 0) {
+        if (nrhs != 8) mexErrMsgIdAndTxt("DESC:b200", "cemp: 7 arguments expected");
+        mwSize m;
+        check_inputs(prhs[1], prhs[2], &m);
+        const int max_iter = (int)mxGetScalar(prhs[3]);
+        if (!mxIsDouble(prhs[4]) || mxIsEmpty(prhs[4]))
+            mexErrMsgIdAndTxt("DESC:b200", "CEMP_parameters.reweighting must be a non-empty double vector");
+        const int nsample = (int)mxGetScalar(prhs[5]);
+        const uint64_t seed = (uint64_t)mxGetScalar(prhs[6]);
+        const int want_R = mxIsLogicalScalarTrue(prhs[7]) || (mxIsNumeric(prhs[7]) && mxGetScalar(prhs[7]) != 0);
+        if (nsample <= 0) mexErrMsgIdAndTxt("DESC:b200", "CEMP_parameters.nsample must be positive");
+        desc_b200_handle* h = NULL;
+        fail_if(desc_b200_create(&h, 0, (int64_t)m, mxGetPr(prhs[1]), mxGetPr(prhs[2]), NULL), NULL);
+        int64_t info[10];
+        fail_if(desc_b200_get_info(h, info), h);
+        mxArray* S = mxCreateDoubleMatrix(1, m, mxREAL);               /* CEMP.m:101: 1 x m row */
+        mxArray* R = NULL;
+        if (want_R) {
+            mwSize dims[3] = {3, 3, 0};
+            dims[2] = (mwSize)info[0];
+            R = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
+        } else {
+            R = mxCreateDoubleMatrix(0, 0, mxREAL);
+        }
+        fail_if(desc_b200_build_incidence(h, nsample, seed, NULL, NULL), h);
+        fail_if(desc_b200_cycle_inconsistency(h), h);
+        fail_if(desc_b200_cemp(h, max_iter, mxGetPr(prhs[4]), (int32_t)mxGetNumberOfElements(prhs[4]), mxGetPr(S)), h);
+        if (want_R) fail_if(desc_b200_cemp_gcw(h, NULL, mxGetPr(R)), h);
+        desc_b200_destroy(h);
+        const char* fields[] = {"SVec", "R_est"};
+        plhs[0] = mxCreateStructMatrix(1, 1, 2, fields);
+        mxSetField(plhs[0], 0, "SVec", S);
+        mxSetField(plhs[0], 0, "R_est", R);
+        return;
+    }
+    if (strcmp(cmd, "align") == 0) {
+        if (nrhs != 3) mexErrMsgIdAndTxt("DESC:b200", "align: 2 arguments expected");
+        const mwSize ne = mxGetNumberOfElements(prhs[1]);
+        if (!mxIsDouble(prhs[1]) || !mxIsDouble(prhs[2]) || ne != mxGetNumberOfElements(prhs[2]) || ne % 9 != 0 || ne < 18)
+            mexErrMsgIdAndTxt("DESC:b200", "R_est and R_gt must both be 3 x 3 x n, n >= 2");
+        const mwSize n = ne / 9;
+        /* the metric needs no graph: a path on n nodes with identity edges carries the device context */
+        mxArray* Ind = mxCreateDoubleMatrix(n - 1, 2, mxREAL);
+        mwSize dims[3] = {3, 3, 0};
+        dims[2] = n - 1;
+        mxArray* Rij = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
+        for (mwSize e = 0; e + 1 < n; e++) {
+            mxGetPr(Ind)[e] = (double)(e + 1);
+            mxGetPr(Ind)[e + (n - 1)] = (double)(e + 2);
+            mxGetPr(Rij)[9 * e] = mxGetPr(Rij)[9 * e + 4] = mxGetPr(Rij)[9 * e + 8] = 1.0;
+        }
+        desc_b200_handle* h = NULL;
+        fail_if(desc_b200_create(&h, 0, (int64_t)(n - 1), mxGetPr(Ind), mxGetPr(Rij), NULL), NULL);
+        dims[2] = n;
+        mxArray* R_out = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
+        mxArray* R_align = mxCreateDoubleMatrix(3, 3, mxREAL);
+        double mean_error = 0.0, median_error = 0.0;
+        fail_if(desc_b200_rotation_alignment(h, mxGetPr(prhs[1]), mxGetPr(prhs[2]), mxGetPr(R_out), mxGetPr(R_align),
+                                             &mean_error, &median_error), h);
+        desc_b200_destroy(h);
+        mxDestroyArray(Ind);
+        mxDestroyArray(Rij);
+        const char* fields[] = {"R_out", "R_align", "mean_error", "median_error"};
+        plhs[0] = mxCreateStructMatrix(1, 1, 4, fields);
+        mxSetField(plhs[0], 0, "R_out", R_out);
+        mxSetField(plhs[0], 0, "R_align", R_align);
+        mxSetField(plhs[0], 0, "mean_error", mxCreateDoubleScalar(mean_error));
+        mxSetField(plhs[0], 0, "median_error", mxCreateDoubleScalar(median_error));
         return;
     }
     mexErrMsgIdAndTxt("DESC:b200", "unknown command '%s'", cmd);

@@ -239,3 +239,135 @@ def gcw_literal(Ind, RijMat, S_vec):
         S0 = np.diag([1.0, 1.0, np.linalg.det(Ur @ Vrt)])
         R_est[:, :, i] = Ur @ S0 @ Vrt
     return R_est
+
+
+def cemp_literal(Ind, RijMat, CEMP_parameters, CoIndMat, return_gcw=False):
+    """Algorithms/CEMP.m:25-131 statement by statement (== CEMP_GCW.m:25-125), dense structures.
+
+    ``CoIndMat`` (nsample x m, 1-based apices, column l used only for edges with a triangle) is what
+    ``datasample(find(AdjMat(:,i).*AdjMat(:,j)), nsample)`` (:63, WITH replacement) returned: MATLAB's
+    RNG cannot be restated, so the draw is an input.  ``return_gcw``: also CEMP_GCW.m:127-159."""
+    Ind = np.asarray(Ind).astype(np.int64)
+    RijMat = np.asarray(RijMat, dtype=np.float64)
+    T = int(CEMP_parameters["max_iter"])                        # :27
+    beta_cemp = [float(b) for b in np.asarray(CEMP_parameters["reweighting"], dtype=np.float64).ravel()]   # :28
+    nsample = int(CEMP_parameters["nsample"])                   # :29
+    T_beta = len(beta_cemp)                                     # :30
+    if T_beta < T:                                              # :31-35
+        beta_cemp = beta_cemp + [beta_cemp[-1]] * (T - T_beta)
+    Ind_i = Ind[:, 0]                                           # :38
+    Ind_j = Ind[:, 1]
+    n = int(Ind.max())                                          # :40
+    m = Ind_i.size                                              # :41
+    AdjMat = np.zeros((n + 1, n + 1))                           # :42-43 (row/col 0 unused)
+    AdjMat[Ind_i, Ind_j] = 1
+    AdjMat = AdjMat + AdjMat.T
+    CoDeg = (AdjMat @ AdjMat) * AdjMat                          # :50
+    AdjPos = AdjMat.copy()                                      # :51
+    AdjPos[CoDeg > 0] = -1                                      # :53
+    AdjPosLow = np.tril(AdjPos[1:, 1:]).flatten(order="F")      # :54
+    AdjPosLow = AdjPosLow[AdjPosLow != 0]                       # :55
+    IndPos = np.nonzero(AdjPosLow < 0)[0] + 1                   # :57 (1-based edge ids)
+    IndPosbin = np.zeros(m + 1, dtype=bool)                     # :58-59
+    IndPosbin[IndPos] = True
+    CoIndMat = np.asarray(CoIndMat).astype(np.int64)
+    assert CoIndMat.shape == (nsample, m)
+    for l in IndPos:                                            # :63 (the draw itself is the input)
+        i, j = Ind_i[l - 1], Ind_j[l - 1]
+        assert (AdjMat[CoIndMat[:, l - 1], i] * AdjMat[CoIndMat[:, l - 1], j] == 1).all()
+    RijMat4d = np.zeros((3, 3, n + 1, n + 1))                   # :69-76
+    IndMat = np.zeros((n + 1, n + 1), dtype=np.int64)
+    for l in range(1, m + 1):
+        i, j = Ind_i[l - 1], Ind_j[l - 1]
+        RijMat4d[:, :, i, j] = RijMat[:, :, l - 1]
+        RijMat4d[:, :, j, i] = RijMat[:, :, l - 1].T
+        IndMat[i, j] = l
+        IndMat[j, i] = -l
+    Rki0 = np.zeros((3, 3, m, nsample))                         # :79-84
+    Rjk0 = np.zeros((3, 3, m, nsample))
+    for l in IndPos:
+        Rki0[:, :, l - 1, :] = RijMat4d[:, :, CoIndMat[:, l - 1], Ind_i[l - 1]]
+        Rjk0[:, :, l - 1, :] = RijMat4d[:, :, Ind_j[l - 1], CoIndMat[:, l - 1]]
+    # :87-89 reshape with the edge index fastest: slot s*m + l
+    Rki0Mat = Rki0.reshape(3, 3, m * nsample, order="F")
+    Rjk0Mat = Rjk0.reshape(3, 3, m * nsample, order="F")
+    Rij0Mat = np.tile(RijMat, (1, 1, nsample))
+    R_cycle0 = np.zeros((3, 3, m * nsample))                    # :91-95
+    R_cycle = np.zeros((3, 3, m * nsample))
+    for j in range(3):
+        R_cycle0 = R_cycle0 + Rij0Mat[:, j, None, :] * Rjk0Mat[j, None, :, :]
+    for j in range(3):                                          # :96-98
+        R_cycle = R_cycle + R_cycle0[:, j, None, :] * Rki0Mat[j, None, :, :]
+    R_trace = ((R_cycle[0, 0, :] + R_cycle[1, 1, :]) + R_cycle[2, 2, :]).reshape(m, nsample, order="F").T   # :99
+    S0Mat = abs_acos((R_trace - 1.0) / 2.0) / np.pi             # :100  (nsample x m)
+    SVec = np.zeros(m + 1)
+    SVec[1:] = S0Mat.mean(axis=0)                               # :101
+    SVec[~IndPosbin] = 1                                        # :102
+    SVec[0] = 0
+    hist = [SVec[1:].copy()]
+    for it in range(T):                                         # :106
+        beta = beta_cemp[it]                                    # :108
+        Ski = np.zeros((nsample, m))                            # :109-110
+        Sjk = np.zeros((nsample, m))
+        for l in IndPos:                                        # :111-115
+            i, j = Ind_i[l - 1], Ind_j[l - 1]
+            Ski[:, l - 1] = SVec[np.abs(IndMat[i, CoIndMat[:, l - 1]])]
+            Sjk[:, l - 1] = SVec[np.abs(IndMat[j, CoIndMat[:, l - 1]])]
+        Smax = Ski + Sjk                                        # :116
+        WeightMat = np.exp(-beta * Smax)                        # :118
+        weightsum = WeightMat.sum(axis=0)                       # :119
+        WeightMat = WeightMat / weightsum[None, :]              # :121
+        SMat = WeightMat * S0Mat                                # :122
+        SVec[1:] = SMat.sum(axis=0)                             # :124
+        SVec[~IndPosbin] = 1                                    # :125
+        SVec[0] = 0
+        hist.append(SVec[1:].copy())
+    out = SVec[1:].copy()
+    if not return_gcw:
+        return out, dict(S0Mat=S0Mat, hist=hist, IndPos=IndPos)
+    # CEMP_GCW.m:127-159: GCW.m with Weights = 1./(SMat_sq+1e-8) (:141)
+    d = 3
+    Rij_blk = np.zeros((n * d, n * d))
+    for k in range(m):
+        i, j = Ind[k, 0] - 1, Ind[k, 1] - 1
+        Rij_blk[3 * i:3 * i + 3, 3 * j:3 * j + 3] = RijMat[:, :, k]
+    Rij_blk = Rij_blk + Rij_blk.T
+    SMat_sq = np.zeros((n, n))
+    SMat_sq[Ind[:, 0] - 1, Ind[:, 1] - 1] = out
+    SMat_sq = SMat_sq + SMat_sq.T
+    Weights = (1.0 / (SMat_sq + 1e-8)) * AdjMat[1:, 1:]         # :141
+    Weights = np.diag(1.0 / Weights.sum(axis=1)) @ Weights      # :142
+    Weights = np.kron(Weights, np.ones((d, d)))
+    RijW = Rij_blk * Weights
+    lam, V = np.linalg.eig(RijW)                                # :148
+    top = np.argsort(-lam.real)[:d]
+    V = np.real(V[:, top])
+    V = V / np.linalg.norm(V, axis=0, keepdims=True)
+    V[:, 0] = V[:, 0] * np.sign(np.linalg.det(V[:d, :]))        # :149
+    R_est = np.zeros((d, d, n))
+    for i in range(n):                                          # :151-157
+        Ur, _, Vrt = np.linalg.svd(V[3 * i:3 * i + 3, :])
+        R_est[:, :, i] = Ur @ np.diag([1.0, 1.0, np.linalg.det(Ur @ Vrt)]) @ Vrt
+    return out, dict(S0Mat=S0Mat, hist=hist, IndPos=IndPos, R_est=R_est)
+
+
+def cemp_draw(Ind, nsample, rng):
+    """A with-replacement draw of CEMP.m:63 (numpy RNG standing in for datasample): returns
+    (CoIndMat nsample x m 1-based, zeros for edges without a triangle; ptr over all edges; apex 0-based)."""
+    Ind = np.asarray(Ind).astype(np.int64)
+    n = int(Ind.max())
+    m = Ind.shape[0]
+    A = np.zeros((n + 1, n + 1), dtype=bool)
+    A[Ind[:, 0], Ind[:, 1]] = True
+    A = A | A.T
+    rng = np.random.default_rng(rng)
+    CoIndMat = np.zeros((nsample, m), dtype=np.int64)
+    cnt = np.zeros(m, dtype=np.int64)
+    for l in range(m):
+        c = np.nonzero(A[:, Ind[l, 0]] & A[:, Ind[l, 1]])[0]
+        if c.size:
+            CoIndMat[:, l] = c[rng.integers(0, c.size, nsample)]
+            cnt[l] = nsample
+    ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    apex = (CoIndMat.T[cnt > 0].ravel() - 1).astype(np.int32)
+    return CoIndMat, ptr, apex

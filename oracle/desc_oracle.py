@@ -483,8 +483,9 @@ def _project_simplex_rows(w, ptr, ns, seg):
     return np.maximum(w - T[seg], 0.0)
 
 
-def pgd(inc: Incidence, S0, iters, rule, patience=30, tol=1e-5, verbose=False, return_w=False):
-    """DESC.m:148-261.  Returns (S_vec (m,), hist (iters_run,2)=[average_change, obj], iters_run)."""
+def pgd(inc: Incidence, S0, iters, rule, patience=30, tol=1e-5, verbose=False, return_w=False, S_hist=None):
+    """DESC.m:148-261.  Returns (S_vec (m,), hist (iters_run,2)=[average_change, obj], iters_run).
+    ``S_hist``: a list that receives a copy of S_vec after every iteration (make_plots diagnostics, :235-239)."""
     m = inc.m
     ptr = inc.rowptr
     ns = np.diff(ptr)
@@ -523,6 +524,8 @@ def pgd(inc: Incidence, S0, iters, rule, patience=30, tol=1e-5, verbose=False, r
         average_change = float(np.mean(np.abs(S_vec - S_last)))  # DESC.m:232
         obj = float(np.dot(wijk, S_vec[inc.e_jk] + S_vec[inc.e_ki]))  # DESC.m:233
         hist.append((average_change, obj))
+        if S_hist is not None:
+            S_hist.append(S_vec.copy())
         iters_run = it
         if verbose:
             print("iter %d: average change in S_vec %f, objective value: %f" % (it, average_change, obj))
@@ -544,13 +547,15 @@ def pgd(inc: Incidence, S0, iters, rule, patience=30, tol=1e-5, verbose=False, r
 # --------------------------------------------------------------------------------------
 
 
-def gcw(Ind, RijMat, S_vec, dense_limit=400):
+def gcw(Ind, RijMat, S_vec, dense_limit=400, power=1.5):
     """Top-3 eigenvectors ('la') of D^-1 (W o R), computed through the similar symmetric matrix
-    D^-1/2 (W o R) D^-1/2, unit 2-norm columns, sign rule GCW.m:28, SVD projection :30-36."""
+    D^-1/2 (W o R) D^-1/2, unit 2-norm columns, sign rule GCW.m:28, SVD projection :30-36.
+    ``power=1.5``: GCW.m:20;  ``power=1``: the weights of CEMP_GCW.m:141, ``1./(S+1e-8)`` (the rest of
+    CEMP_GCW.m:127-159 is GCW.m line for line)."""
     n, ei, ej = check_ind(Ind)
     R = to_internal(RijMat)
     S_vec = np.asarray(S_vec, dtype=np.float64).ravel()
-    om = 1.0 / (S_vec ** 1.5 + 1e-8)                            # GCW.m:20
+    om = 1.0 / ((S_vec ** 1.5 if power == 1.5 else S_vec) + 1e-8)   # GCW.m:20 / CEMP_GCW.m:141
     d = np.bincount(ei, om, n) + np.bincount(ej, om, n)          # sum(Weights,2), GCW.m:21
     isd = 1.0 / np.sqrt(d)
     c = (om * isd[ei] * isd[ej])[:, None, None]
@@ -774,3 +779,102 @@ def DESC(Ind, RijMat, params, **kw):
     """Algorithms/DESC.m:14.  Returns (R_est, R_init, S_vec)."""
     R_init, S_vec = DESC_init(Ind, RijMat, params, **kw)
     return laa_refine(Ind, RijMat, S_vec, R_init), R_init, S_vec
+
+
+# --------------------------------------------------------------------------------------------
+# SURVEY 8(f) #3: CEMP / CEMP+GCW on the same incidence (Algorithms/CEMP.m, CEMP_GCW.m)
+# --------------------------------------------------------------------------------------------
+def cemp_incidence(Ind, nsample=50, seed=0, cycles=None):
+    """Cycle lists for CEMP as an ``Incidence`` (IKJ/JKI unused, left empty).
+
+    CEMP.m:63 draws ``datasample(find(...), nsample)`` -- WITH replacement, so every edge with a
+    triangle gets exactly ``nsample`` slots and an apex may repeat.  MATLAB's RNG stream cannot be
+    restated; as for DESC (module header) the stand-in is the shared counter-based sampler
+    (``nsample`` smallest keys, no repeats, at most co-degree slots), or explicit ``(ptr, apex)`` lists
+    over ALL edges, which MAY contain repeated apices (e.g. the CoIndMat a MATLAB run drew)."""
+    if cycles is None:
+        return build_incidence(Ind, n_sample=int(nsample), seed=seed)
+    n, ei, ej = check_ind(Ind)
+    m = ei.size
+    ptr = np.asarray(cycles[0], dtype=np.int64)
+    apex = np.asarray(cycles[1], dtype=np.int64)
+    cnt = np.diff(ptr)
+    sl_e = np.repeat(np.arange(m, dtype=np.int64), cnt)
+    ekey = ei * n + ej
+
+    def edge_id(a, b):
+        lo, hi = np.minimum(a, b), np.maximum(a, b)
+        idx = np.searchsorted(ekey, lo * n + hi)
+        if not (idx < m).all() or not (ekey[np.minimum(idx, m - 1)] == lo * n + hi).all():
+            raise ValueError("explicit cycle list contains an apex that is not a common neighbour")
+        return idx
+
+    e_jk = edge_id(ej[sl_e], apex)
+    e_ki = edge_id(apex, ei[sl_e])
+    pos_edges = np.nonzero(cnt > 0)[0]
+    rowptr = np.concatenate([[0], np.cumsum(cnt[pos_edges])]).astype(np.int64)
+    none = np.zeros(0, np.int64)
+    return Incidence(n=n, m=m, ei=ei, ej=ej, codeg=cnt.copy(), n_sample=int(cnt.max()) if m else 0,
+                     pos_edges=pos_edges, rowptr=rowptr, e_ij=sl_e, e_jk=e_jk, e_ki=e_ki, k=apex, IKJ=none, JKI=none)
+
+
+def cemp_betas(max_iter, reweighting):
+    """CEMP.m:26-34: a short reweighting vector is padded with its last element."""
+    beta = [float(b) for b in np.asarray(reweighting, dtype=np.float64).ravel()]
+    T = int(max_iter)
+    if len(beta) < T:
+        beta = beta + [beta[-1]] * (T - len(beta))
+    return beta[:T]
+
+
+def cemp_reweight(inc: Incidence, S0, SVec, beta, empty_value=1.0):
+    """One CEMP reweighting (CEMP.m:109-125): per edge, ``sum_s w_s/sum(w) * S0_s`` with
+    ``w_s = exp(-beta*(SVec(e_ki)+SVec(e_jk)))``; edges without cycles get ``empty_value`` (:125)."""
+    seg = inc.rowptr[:-1]
+    Smax = SVec[inc.e_ki] + SVec[inc.e_jk]                                   # Ski+Sjk, :117
+    W = np.exp(-beta * Smax)                                                  # :119
+    out = np.full(inc.m, empty_value, dtype=np.float64)
+    if inc.m_pos:
+        wsum = np.add.reduceat(W, seg)                                        # :120
+        Wn = W / np.repeat(wsum, np.diff(inc.rowptr))                         # :122
+        out[inc.pos_edges] = np.add.reduceat(Wn * S0, seg)                    # :123-125
+    return out
+
+
+def cemp(inc: Incidence, S0, max_iter, reweighting, return_hist=False):
+    """Algorithms/CEMP.m:98-129 on CSR slot lists.  Returns SVec (length m)."""
+    SVec = np.ones(inc.m, dtype=np.float64)
+    if inc.m_pos:
+        SVec[inc.pos_edges] = np.add.reduceat(S0, inc.rowptr[:-1]) / np.diff(inc.rowptr)   # mean(S0Mat,1), :99
+    hist = [SVec.copy()]
+    for beta in cemp_betas(max_iter, reweighting):
+        SVec = cemp_reweight(inc, S0, SVec, beta)
+        hist.append(SVec.copy())
+    return (SVec, hist) if return_hist else SVec
+
+
+def CEMP(Ind, RijMat, CEMP_parameters, seed=0, cycles=None):
+    """``SVec = CEMP(Ind, RijMat, CEMP_parameters)`` (Algorithms/CEMP.m:25)."""
+    inc = cemp_incidence(Ind, CEMP_parameters["nsample"], seed=seed, cycles=cycles)
+    S0 = cycle_inconsistency(inc, RijMat)
+    return cemp(inc, S0, CEMP_parameters["max_iter"], CEMP_parameters["reweighting"])
+
+
+def CEMP_GCW(Ind, RijMat, CEMP_parameters, seed=0, cycles=None):
+    """``R_est = CEMP_GCW(Ind, RijMat, CEMP_parameters)`` (Algorithms/CEMP_GCW.m:25)."""
+    return gcw(Ind, RijMat, CEMP(Ind, RijMat, CEMP_parameters, seed=seed, cycles=cycles), power=1.0)
+
+
+# --------------------------------------------------------------------------------------------
+# SURVEY 8(f) #4: the make_plots diagnostics of DESC.m:235-239 (per-iteration S_vec error + GCW + alignment)
+# --------------------------------------------------------------------------------------------
+def pgd_diagnostics(Ind, RijMat, S_hist, ErrVec, R_orig):
+    """For every iteration's S_vec: ``mean(abs(ErrVec - S_vec))`` (DESC.m:236), ``GCW`` (:237) and the
+    mean / median alignment error in degrees (:238, Utils/GlobalSOdCorrectRight.m == Rotation_Alignment.m)."""
+    ErrVec = np.asarray(ErrVec, dtype=np.float64).ravel()
+    out = np.zeros((len(S_hist), 3))
+    for t, S in enumerate(S_hist):
+        R = gcw(Ind, RijMat, S)
+        _, _, mean_err, med_err = rotation_alignment(R, R_orig)
+        out[t] = [float(np.mean(np.abs(ErrVec - S))), mean_err, med_err]
+    return out

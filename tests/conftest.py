@@ -16,8 +16,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-def golden_names():
+def _all_golden():
     return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def golden_names():
+    """the DESC fixtures (DESC.m:14-312)"""
+    return [n for n in _all_golden() if not n.startswith("cemp_")]
+
+
+def cemp_golden_names():
+    """the CEMP / CEMP_GCW fixtures (CEMP.m, CEMP_GCW.m)"""
+    return [n for n in _all_golden() if n.startswith("cemp_")]
 
 
 def load_golden(name):

@@ -14,6 +14,15 @@ Each ``.npz`` holds the inputs (Ind, RijMat, R_orig, ErrVec, params) and the lit
 (incidence arrays, S0_long, wijk, S_vec, hist, iters_run, R_est of GCW) and, for the whole ``DESC()``
 call, the refinement stage DESC.m:265-312 started from them (R_laa, laa_scores; oracle.laa_refine, a
 statement-by-statement restatement of the loop and of Utils/Weighted_LAA.m).
+
+``cemp_*.npz`` hold a with-replacement draw ``CoIndMat`` standing in for CEMP.m:63 (MATLAB's
+``datasample`` stream cannot be restated, so the draw is part of the fixture), the literal CEMP.m / CEMP_GCW.m
+outputs on it (``S0Mat``, ``SVec`` after every reweighting, ``R_est``) and the alignment metric
+(Utils/Rotation_Alignment.m) of ``R_est`` against ``R_orig``.  A MATLAB user can replay them by replacing the
+``datasample`` call with the stored ``CoIndMat`` column.
+
+    python tests/golden/make_golden.py            # everything
+    python tests/golden/make_golden.py cemp       # only the fixtures whose name starts with "cemp"
 """
 import os
 import sys
@@ -24,7 +33,7 @@ import scipy.io
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import desc_oracle as O          # noqa: E402
-from oracle.desc_literal import desc_literal  # noqa: E402
+from oracle.desc_literal import desc_literal, cemp_literal, cemp_draw  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -45,6 +54,34 @@ CASES = [
 ]
 
 
+CEMP_CASES = [
+    # name, generator args, CEMP_parameters, draw seed
+    ("cemp_uniform_n40", dict(n=40, p=0.5, q=0.25, sigma=0.05, model="uniform"),
+     dict(max_iter=6, reweighting=[1.0, 2.0, 4.0, 8.0, 16.0, 32.0], nsample=12), 5),
+    ("cemp_uniform_n36_shortbeta", dict(n=36, p=0.3, q=0.2, sigma=0.0, model="uniform"),
+     dict(max_iter=5, reweighting=[1.0, 3.0], nsample=7), 6),
+]
+
+
+def make_cemp(prefix):
+    for idx, (name, a, P, dseed) in enumerate(CEMP_CASES):
+        if not name.startswith(prefix):
+            continue
+        mo = O.uniform_topology(a["n"], a["p"], a["q"], a["sigma"], a["model"], rng=np.random.default_rng(2000 + idx))
+        Co, ptr, apex = cemp_draw(mo["Ind"], P["nsample"], dseed)
+        SVec, ex = cemp_literal(mo["Ind"], mo["RijMat"], P, Co, return_gcw=True)
+        _, R_align, mean_err, med_err = O.rotation_alignment(ex["R_est"], mo["R_orig"])
+        out = dict(Ind=mo["Ind"], RijMat=mo["RijMat"], R_orig=mo["R_orig"], ErrVec=mo["ErrVec"],
+                   max_iter=np.int64(P["max_iter"]), reweighting=np.array(P["reweighting"], dtype=np.float64),
+                   nsample=np.int64(P["nsample"]), CoIndMat=Co, cyc_ptr=ptr, cyc_apex=apex, S0Mat=ex["S0Mat"],
+                   SVec=SVec, SVec_hist=np.array(ex["hist"]), R_est=ex["R_est"], R_align=R_align,
+                   mean_error=np.float64(mean_err), median_error=np.float64(med_err))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        scipy.io.savemat(os.path.join(HERE, name + ".mat"), out, do_compression=True)
+        print("%-26s n=%d m=%d slots=%d mean|SVec-ErrVec| %.4g  CEMP+GCW error %.4g / %.4g deg" % (
+            name, a["n"], mo["Ind"].shape[0], apex.size, np.mean(np.abs(SVec - mo["ErrVec"])), mean_err, med_err))
+
+
 def make_rule(spec):
     if spec[0] == "const":
         return O.ConstantStepSize(spec[1])
@@ -54,7 +91,11 @@ def make_rule(spec):
 
 
 def main():
+    prefix = sys.argv[1] if len(sys.argv) > 1 else ""
+    make_cemp(prefix)
     for idx, (name, gen, args, ns, seed, rule_spec, iters) in enumerate(CASES):
+        if not name.startswith(prefix):
+            continue
         rng = np.random.default_rng(1000 + idx)
         a = dict(args)
         n = a.pop("n")

@@ -25,7 +25,7 @@ def test_library_exports_every_header_symbol():
     lib = _lib.load()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.desc_b200_version() == 100
+    assert lib.desc_b200_version() == 101
 
 
 def test_struct_layouts_match_header(tmp_path):
@@ -33,14 +33,16 @@ def test_struct_layouts_match_header(tmp_path):
     src = tmp_path / "sz.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "desc_b200.h"\n'
-        'int main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(desc_b200_opts), sizeof(desc_b200_step_rule),'
+        'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(desc_b200_opts), sizeof(desc_b200_step_rule),'
         ' sizeof(desc_b200_timings), offsetof(desc_b200_step_rule,t), offsetof(desc_b200_opts,nccl_id),'
-        ' offsetof(desc_b200_timings,pgd_launches), offsetof(desc_b200_opts,stream));return 0;}\n')
+        ' offsetof(desc_b200_timings,pgd_launches), offsetof(desc_b200_opts,stream),'
+        ' offsetof(desc_b200_timings,cemp_ms));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     mine = [C.sizeof(_lib.Opts), C.sizeof(_lib.StepRule), C.sizeof(_lib.Timings), _lib.StepRule.t.offset,
-            _lib.Opts.nccl_id.offset, _lib.Timings.pgd_launches.offset, _lib.Opts.stream.offset]
+            _lib.Opts.nccl_id.offset, _lib.Timings.pgd_launches.offset, _lib.Opts.stream.offset,
+            _lib.Timings.cemp_ms.offset]
     assert got == mine
 
 
@@ -49,7 +51,8 @@ def test_mex_gateway_compiles_against_stub_header():
                         "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "mex", "desc_b200_mex.c")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    for shim in ("DESC.m", "DESC_PGD.m", "DESC_init.m", "GCW.m", "desc_b200_rule.m", "desc_b200_run.m"):
+    for shim in ("DESC.m", "DESC_PGD.m", "DESC_init.m", "GCW.m", "CEMP.m", "CEMP_GCW.m", "Rotation_Alignment.m",
+                 "desc_b200_rule.m", "desc_b200_run.m"):
         assert os.path.exists(os.path.join(ROOT, "matlab", shim))
 
 
@@ -74,9 +77,11 @@ def test_host_side_argument_checks():
         desc_b200.Solver(np.array([[1.0, 2.0]]), np.zeros((3, 3, 2)))
     with pytest.raises(ValueError):
         desc_b200.DESC_PGD(np.array([[1.0, 2.0]]), np.zeros((3, 3, 1)), dict(iters=1, Gradient=None))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):   # make_plots needs ErrVec and R_orig (DESC.m:236-238)
         desc_b200.DESC_PGD(np.array([[1.0, 2.0]]), np.zeros((3, 3, 1)),
                            dict(iters=1, Gradient=desc_b200.ConstantStepSize(1.0), make_plots=True))
+    with pytest.raises(ValueError):
+        desc_b200.Rotation_Alignment(np.zeros((3, 3, 1)), np.zeros((3, 3, 1)))
 
 
 def test_no_gpu_means_loud_failure_not_fallback():

@@ -236,3 +236,79 @@ def test_oracle_laa_reproduces_golden(name):
     R, info = O.laa_refine(g["Ind"], g["RijMat"], g["S_vec"], g["R_est"], return_info=True)
     np.testing.assert_allclose(info["scores"], g["laa_scores"], rtol=1e-9, atol=1e-13)
     assert O.aligned_angle_deg(R, g["R_laa"]).mean() <= 1e-9
+
+
+# ---- CEMP on the same incidence, alignment metric, make_plots diagnostics ----
+from conftest import cemp_golden_names  # noqa: E402
+
+
+@pytest.mark.parametrize("name", cemp_golden_names())
+def test_csr_cemp_oracle_matches_literal_golden(name):
+    """CSR restatement of CEMP.m / CEMP_GCW.m vs the literal dense one, on the fixture's with-replacement draw
+    (cycle lists with repeated apices)."""
+    g = load_golden(name)
+    inc = O.cemp_incidence(g["Ind"], cycles=(g["cyc_ptr"], g["cyc_apex"]))
+    S0 = O.cycle_inconsistency(inc, g["RijMat"])
+    ns = int(g["nsample"])
+    pos = np.diff(g["cyc_ptr"]) > 0
+    np.testing.assert_array_equal(S0.reshape(-1, ns).T, g["S0Mat"][:, pos])     # same operation order
+    SVec, hist = O.cemp(inc, S0, int(g["max_iter"]), g["reweighting"], return_hist=True)
+    assert len(hist) == int(g["max_iter"]) + 1
+    np.testing.assert_allclose(np.array(hist), g["SVec_hist"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(SVec, g["SVec"], rtol=1e-12, atol=1e-15)
+    assert (SVec[~pos] == 1.0).all()                                             # CEMP.m:102,125
+    R = O.gcw(g["Ind"], g["RijMat"], SVec, power=1.0)
+    assert O.aligned_angle_deg(R, g["R_est"]).mean() < 1e-6
+    _, R_align, mean_err, med_err = O.rotation_alignment(g["R_est"], g["R_orig"])
+    assert abs(mean_err - float(g["mean_error"])) < 1e-12 and abs(med_err - float(g["median_error"])) < 1e-12
+
+
+def test_cemp_known_answers():
+    # clean graph: every cycle is consistent -> SVec = 0 on edges with a triangle, 1 elsewhere
+    mo = O.uniform_topology(50, 0.35, 0.0, 0.0, rng=4)
+    P = dict(max_iter=4, reweighting=[1.0, 2.0], nsample=10)
+    SVec = O.CEMP(mo["Ind"], mo["RijMat"], P, seed=2)
+    inc = O.cemp_incidence(mo["Ind"], 10, seed=2)
+    has = np.zeros(inc.m, bool)
+    has[inc.pos_edges] = True
+    assert np.all(SVec[has] < 1e-7) and np.all(SVec[~has] == 1.0)
+    # beta padding CEMP.m:31-35
+    assert O.cemp_betas(5, [1.0, 3.0]) == [1.0, 3.0, 3.0, 3.0, 3.0]
+    assert O.cemp_betas(2, [1.0, 2.0, 4.0]) == [1.0, 2.0]
+    # beta = 0: every reweighting returns the plain mean of the edge's d_ijk
+    mo = O.uniform_topology(40, 0.5, 0.3, 0.1, rng=5)
+    inc = O.cemp_incidence(mo["Ind"], 8, seed=0)
+    S0 = O.cycle_inconsistency(inc, mo["RijMat"])
+    S_a = O.cemp(inc, S0, 0, [1.0])
+    S_b = O.cemp(inc, S0, 3, [0.0])
+    np.testing.assert_allclose(S_a, S_b, rtol=1e-14)
+    # with corruption CEMP separates corrupted from clean edges (sigma = 0: clean edges go to ~0)
+    mo = O.uniform_topology(80, 0.5, 0.2, 0.0, rng=6)
+    SVec = O.CEMP(mo["Ind"], mo["RijMat"], dict(max_iter=6, reweighting=2.0 ** np.arange(6), nsample=30), seed=1)
+    clean = mo["ErrVec"] == 0
+    assert np.mean(np.abs(SVec - mo["ErrVec"])) < 0.01 and SVec[clean].max() < 0.05
+
+
+def test_rotation_alignment_known_answer():
+    rng = np.random.default_rng(8)
+    R = O.to_matlab(O._rand_rot(30, rng))
+    Q = O._rand_rot(1, rng)[0]
+    R_rot = O.to_matlab(O.to_internal(R) @ Q)               # every rotation right-multiplied by the same Q
+    R_out, R_align, mean_err, med_err = O.rotation_alignment(R_rot, R)
+    np.testing.assert_allclose(R_align, Q.T, atol=1e-12)
+    np.testing.assert_allclose(R_out, R, atol=1e-12)
+    assert mean_err < 1e-5 and med_err < 1e-5
+
+
+def test_pgd_diagnostics_follow_the_iterates():
+    mo = O.uniform_topology(40, 0.5, 0.2, 0.1, rng=9)
+    inc = O.build_incidence(mo["Ind"], n_sample=10, seed=0)
+    S0 = O.cycle_inconsistency(inc, mo["RijMat"])
+    S_hist = []
+    S_vec, hist, iters_run = O.pgd(inc, S0, 5, O.ConstantStepSize(0.05), S_hist=S_hist)
+    assert len(S_hist) == iters_run == 5 and np.array_equal(S_hist[-1], S_vec)
+    d = O.pgd_diagnostics(mo["Ind"], mo["RijMat"], S_hist, mo["ErrVec"], mo["R_orig"])
+    assert d.shape == (5, 3)
+    assert d[-1, 0] == pytest.approx(np.mean(np.abs(mo["ErrVec"] - S_vec)))
+    R = O.gcw(mo["Ind"], mo["RijMat"], S_vec)
+    assert d[-1, 1] == pytest.approx(O.rotation_alignment(R, mo["R_orig"])[2])
