@@ -27,6 +27,8 @@ SYMBOLS = [
     "desc_b200_get_gcw_info", "desc_b200_get_timings", "desc_b200_sync",
     "desc_b200_cemp", "desc_b200_cemp_gcw", "desc_b200_cycle_reweight", "desc_b200_rotation_alignment",
     "desc_b200_pgd_diag",
+    "desc_b200_generate", "desc_b200_model_destroy", "desc_b200_model_info", "desc_b200_model_fetch",
+    "desc_b200_model_device",
 ]
 
 
@@ -41,6 +43,13 @@ class DescError(RuntimeError):
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("stream", C.c_void_p), ("rank", C.c_int32),
                 ("world", C.c_int32), ("nccl_id", C.c_void_p)]
+
+
+class GenOpts(C.Structure):
+    _fields_ = [("device", C.c_int32), ("topology", C.c_int32), ("n", C.c_int32), ("window", C.c_int32),
+                ("kind", C.c_int32), ("reserved", C.c_int32), ("p", C.c_double), ("q", C.c_double),
+                ("sigma", C.c_double), ("sigma_out", C.c_double), ("p_node_crpt", C.c_double),
+                ("p_edge_crpt", C.c_double), ("seed", C.c_uint64)]
 
 
 class StepRule(C.Structure):
@@ -97,6 +106,12 @@ def load():
     lib.desc_b200_get_gcw_info.argtypes = [vp, C.POINTER(C.c_double)]
     lib.desc_b200_get_timings.argtypes = [vp, C.POINTER(Timings)]
     lib.desc_b200_sync.argtypes = [vp]
+    lib.desc_b200_generate.argtypes = [C.POINTER(GenOpts), C.POINTER(vp)]
+    lib.desc_b200_model_destroy.argtypes = [vp]
+    lib.desc_b200_model_destroy.restype = None
+    lib.desc_b200_model_info.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_double)]
+    lib.desc_b200_model_fetch.argtypes = [vp, dp, dp, dp, dp, dp, vp]
+    lib.desc_b200_model_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.desc_b200_cemp.argtypes = [vp, i32, dp, i32, dp]
     lib.desc_b200_cemp_gcw.argtypes = [vp, dp, dp]
     lib.desc_b200_cycle_reweight.argtypes = [vp, dp, C.c_double, C.c_double, dp]

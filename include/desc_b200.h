@@ -211,6 +211,37 @@ int desc_b200_rotation_alignment(desc_b200_handle* h, const double* R_est, const
 int desc_b200_pgd_diag(desc_b200_handle* h, int32_t iters, desc_b200_step_rule* rule, const double* ErrVec,
                        const double* R_orig, double* S_vec_out, double* hist_out, double* diag_out,
                        int32_t* iters_run_out);
+
+/* ---- the reference's data generators on the device ----
+   Models/Uniform_Topology.m:24 `Uniform_Topology(n,p,q,sigma,model)` (kind 0: model 'uniform', kind 1: any other
+   model string = self-consistent corruption) and Models/Nonuniform_Topology.m:26
+   `Nonuniform_Topology(n,p,p_node_crpt,p_edge_crpt,sigma_in,sigma_out,crpt_type)` (kind 2 'uniform',
+   3 'self-consistent', 4 'adv'; sigma = sigma_in).  topology 1 restricts the Erdos-Renyi draw to pairs whose
+   circular distance is <= window (SfM-shaped graphs, BASELINE.json configs[4]; kinds 0/1 only).  MATLAB's RNG
+   stream is replaced by counter-based draws of `seed` (csrc/gen.cu).  The model owns device buffers in exactly the
+   layout desc_b200_create takes with DESC_B200_INPUTS_ON_DEVICE.                                             */
+typedef struct desc_b200_model desc_b200_model;
+typedef struct desc_b200_gen_opts {
+    int32_t device;       /* CUDA device ordinal; -1 = current device */
+    int32_t topology;     /* 0 Erdos-Renyi G(n,p); 1 ring window       */
+    int32_t n;
+    int32_t window;
+    int32_t kind;
+    int32_t reserved;
+    double p, q, sigma, sigma_out, p_node_crpt, p_edge_crpt;
+    uint64_t seed;
+} desc_b200_gen_opts;
+int desc_b200_generate(const desc_b200_gen_opts* opts, desc_b200_model** out);
+void desc_b200_model_destroy(desc_b200_model* mo);
+/* info[0]=n, [1]=m, [2]=kernels launched, [3]=device; gen_ms (may be NULL): device time of the generation */
+int desc_b200_model_info(desc_b200_model* mo, int64_t info[4], double* gen_ms);
+/* copies to host buffers (any may be NULL): Ind 2m, RijMat 9m, R_orig 9n, ErrVec m, Rij_orig 9m, corrupted m bytes
+   (the reference's corrIndLog / crptInd) */
+int desc_b200_model_fetch(desc_b200_model* mo, double* Ind, double* RijMat, double* R_orig, double* ErrVec,
+                          double* Rij_orig, uint8_t* corrupted);
+/* device pointers of the model's buffers (valid until desc_b200_model_destroy) */
+int desc_b200_model_device(desc_b200_model* mo, const double** Ind, const double** RijMat, const double** R_orig,
+                           const double** ErrVec);
 int desc_b200_get_timings(desc_b200_handle* h, desc_b200_timings* t);
 /* synchronise the handle's stream (for callers timing from outside) */
 int desc_b200_sync(desc_b200_handle* h);

@@ -11,6 +11,9 @@
  *          out.mean_error, out.median_error)
  *   R   = desc_b200_mex('gcw',   Ind, RijMat, S_vec)
  *   out = desc_b200_mex('refine', Ind, RijMat, S_vec, R_init)    (DESC.m:265-312; out.R_est, out.scores)
+ *   mo  = desc_b200_mex('generate', kind, topology, n, window, p, q, sigma, sigma_out, p_node_crpt, p_edge_crpt, seed)
+ *         (Models/Uniform_Topology.m / Nonuniform_Topology.m on the device: mo.Ind, mo.RijMat, mo.Rij_orig,
+ *          mo.R_orig, mo.ErrVec, mo.AdjMat)
  *   n   = desc_b200_mex('device_count')
  *
  * 'solve' runs Algorithms/DESC.m:14-263 (== DESC_PGD.m:14-261 / DESC_init.m:14-253) on the GPU and
@@ -192,6 +195,58 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         plhs[0] = mxCreateStructMatrix(1, 1, 2, fields);
         mxSetField(plhs[0], 0, "R_est", R);
         mxSetField(plhs[0], 0, "scores", scores);
+        return;
+    }
+    if (strcmp(cmd, "generate") == 0) {
+        if (nrhs != 12) mexErrMsgIdAndTxt("DESC:b200", "generate: 11 arguments expected");
+        desc_b200_gen_opts o;
+        memset(&o, 0, sizeof(o));
+        o.device = -1;
+        o.kind = (int32_t)mxGetScalar(prhs[1]);
+        o.topology = (int32_t)mxGetScalar(prhs[2]);
+        o.n = (int32_t)mxGetScalar(prhs[3]);
+        o.window = (int32_t)mxGetScalar(prhs[4]);
+        o.p = mxGetScalar(prhs[5]);
+        o.q = mxGetScalar(prhs[6]);
+        o.sigma = mxGetScalar(prhs[7]);
+        o.sigma_out = mxGetScalar(prhs[8]);
+        o.p_node_crpt = mxGetScalar(prhs[9]);
+        o.p_edge_crpt = mxGetScalar(prhs[10]);
+        o.seed = (uint64_t)mxGetScalar(prhs[11]);
+        desc_b200_model* mo = NULL;
+        fail_if(desc_b200_generate(&o, &mo), NULL);
+        int64_t info[4];
+        int rc = desc_b200_model_info(mo, info, NULL);
+        if (rc != DESC_B200_OK) {
+            desc_b200_model_destroy(mo);
+            fail_if(rc, NULL);
+        }
+        const mwSize n = (mwSize)info[0], m = (mwSize)info[1];
+        mwSize dm[3] = {3, 3, 0}, dn[3] = {3, 3, 0};
+        dm[2] = m;
+        dn[2] = n;
+        mxArray* Ind = mxCreateDoubleMatrix(m, 2, mxREAL);
+        mxArray* Rij = mxCreateNumericArray(3, dm, mxDOUBLE_CLASS, mxREAL);
+        mxArray* Rij0 = mxCreateNumericArray(3, dm, mxDOUBLE_CLASS, mxREAL);
+        mxArray* Ro = mxCreateNumericArray(3, dn, mxDOUBLE_CLASS, mxREAL);
+        mxArray* Err = mxCreateDoubleMatrix(1, m, mxREAL);
+        rc = desc_b200_model_fetch(mo, mxGetPr(Ind), mxGetPr(Rij), mxGetPr(Ro), mxGetPr(Err), mxGetPr(Rij0), NULL);
+        desc_b200_model_destroy(mo);
+        fail_if(rc, NULL);
+        mxArray* Adj = mxCreateDoubleMatrix(n, n, mxREAL);            /* Uniform_Topology.m:32 */
+        for (mwSize e = 0; e < m; e++) {
+            const mwSize i = (mwSize)mxGetPr(Ind)[e] - 1, j = (mwSize)mxGetPr(Ind)[e + m] - 1;
+            mxGetPr(Adj)[i + n * j] = 1.0;
+            mxGetPr(Adj)[j + n * i] = 1.0;
+        }
+        const char* fields[] = {"AdjMat", "Ind", "RijMat", "Rij_orig", "R_orig", "ErrVec"};
+        plhs[0] = mxCreateStructMatrix(1, 1, 6, fields);
+        mxSetField(plhs[0], 0, "AdjMat", Adj);
+        mxSetField(plhs[0], 0, "Ind", Ind);
+        mxSetField(plhs[0], 0, "RijMat", Rij);
+        mxSetField(plhs[0], 0, "Rij_orig", Rij0);
+        mxSetField(plhs[0], 0, "R_orig", Ro);
+        mxSetField(plhs[0], 0, "ErrVec", Err);
         return;
     }
     if (strcmp(cmd, "cemp") == 0) {

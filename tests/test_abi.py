@@ -36,13 +36,15 @@ def test_struct_layouts_match_header(tmp_path):
         'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(desc_b200_opts), sizeof(desc_b200_step_rule),'
         ' sizeof(desc_b200_timings), offsetof(desc_b200_step_rule,t), offsetof(desc_b200_opts,nccl_id),'
         ' offsetof(desc_b200_timings,pgd_launches), offsetof(desc_b200_opts,stream),'
-        ' offsetof(desc_b200_timings,cemp_ms));return 0;}\n')
+        ' offsetof(desc_b200_timings,cemp_ms));'
+        'printf("%zu %zu %zu\\n", sizeof(desc_b200_gen_opts), offsetof(desc_b200_gen_opts,p), offsetof(desc_b200_gen_opts,seed));'
+        'return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     mine = [C.sizeof(_lib.Opts), C.sizeof(_lib.StepRule), C.sizeof(_lib.Timings), _lib.StepRule.t.offset,
             _lib.Opts.nccl_id.offset, _lib.Timings.pgd_launches.offset, _lib.Opts.stream.offset,
-            _lib.Timings.cemp_ms.offset]
+            _lib.Timings.cemp_ms.offset, C.sizeof(_lib.GenOpts), _lib.GenOpts.p.offset, _lib.GenOpts.seed.offset]
     assert got == mine
 
 
@@ -52,6 +54,7 @@ def test_mex_gateway_compiles_against_stub_header():
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     for shim in ("DESC.m", "DESC_PGD.m", "DESC_init.m", "GCW.m", "CEMP.m", "CEMP_GCW.m", "Rotation_Alignment.m",
+                 "Uniform_Topology.m", "Nonuniform_Topology.m",
                  "desc_b200_rule.m", "desc_b200_run.m"):
         assert os.path.exists(os.path.join(ROOT, "matlab", shim))
 
@@ -107,3 +110,64 @@ def test_sampler_key_known_answer():
     z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2 ** 64 - 1)
     z ^= z >> 31
     assert int(sampler_keys(0, 0, 0)) == z
+
+
+def test_generator_argument_checks_and_loud_failure():
+    """SURVEY 8f #2: bad options are rejected by the library; without a device the generators fail loudly"""
+    with pytest.raises(ValueError):
+        desc_b200.Nonuniform_Topology(10, 0.5, 0.3, 0.5, 0.1, 0.1, crpt_type="nonsense")
+    for bad in (dict(n=1, p=0.5, q=0.1, sigma=0.0), dict(n=10, p=0.0, q=0.1, sigma=0.0),
+                dict(n=10, p=0.5, q=1.5, sigma=0.0), dict(n=10, p=0.5, q=0.1, sigma=-1.0)):
+        with pytest.raises(desc_b200.DescError) as e:
+            desc_b200.Uniform_Topology(bad["n"], bad["p"], bad["q"], bad["sigma"])
+        assert e.value.code == _lib.ERR_ARG
+    if _lib.load().desc_b200_device_count() <= 0:
+        with pytest.raises(desc_b200.DescError) as e:
+            desc_b200.Uniform_Topology(20, 0.5, 0.2, 0.1)
+        assert e.value.code == _lib.ERR_CUDA
+
+
+def test_counter_rng_known_answers():
+    """the counter-based draws csrc/gen.cu and oracle/desc_models_ctr.py share: pinned values + distribution"""
+    from oracle import desc_models_ctr as M
+    from oracle.desc_oracle import sampler_keys
+    assert int(M.u64(0, M.S_ADJ, 0, 0)) == int(sampler_keys(0xA0761D6478BD642F, 0, 0))
+    u = M.uniform(3, M.S_MASK, np.arange(100000), 0)
+    assert 0.0 <= u.min() and u.max() < 1.0 and abs(u.mean() - 0.5) < 5e-3
+    z = M.normal(3, M.S_NOISE, np.arange(50000)[:, None], np.arange(9)[None, :])
+    assert abs(z.mean()) < 1e-2 and abs(z.var() - 1.0) < 2e-2 and abs((z ** 4).mean() - 3.0) < 0.1
+    R = M.rand_rot(1, M.S_RORIG, np.arange(50))
+    np.testing.assert_allclose(R @ R.transpose(0, 2, 1), np.broadcast_to(np.eye(3), (50, 3, 3)), atol=1e-13)
+    np.testing.assert_allclose(np.linalg.det(R), 1.0, atol=1e-13)
+
+
+def test_counter_generators_follow_the_reference_structure():
+    from oracle import desc_models_ctr as M
+    from oracle import desc_oracle as O
+    mo = M.uniform_topology(80, 0.4, 0.25, 0.0, "uniform", seed=5)
+    O.check_ind(mo["Ind"])                                            # i<j, (i,j)-sorted: Uniform_Topology.m:33-34
+    assert abs(mo["corrupted"].mean() - 0.25) < 0.05
+    assert mo["ErrVec"][~mo["corrupted"]].max() < 1e-7                # sigma = 0: inliers are exact
+    assert np.median(mo["ErrVec"][mo["corrupted"]]) > 0.4
+    # self-consistent corruption: corrupted edges are mutually consistent (cycle of three corrupted edges closes)
+    mo = M.uniform_topology(60, 0.6, 1.0, 0.0, "self-consistent", seed=6)
+    inc = O.build_incidence(mo["Ind"], n_sample=5, seed=0)
+    assert O.cycle_inconsistency(inc, mo["RijMat"]).max() < 1e-6
+    # ring: only pairs within the window; mean degree ~ deg
+    mo = M.uniform_topology(300, 30 / 80.0, 0.1, 0.05, "uniform", seed=7, ring=40)
+    i, j = mo["Ind"][:, 0] - 1, mo["Ind"][:, 1] - 1
+    d = j - i
+    assert np.all(np.minimum(d, 300 - d) <= 40) and abs(2 * len(i) / 300 - 30) < 3
+    # Nonuniform: floor(n p_node) corrupted nodes, each corrupting floor(p_edge deg) of its edges
+    n = 90
+    mo = M.nonuniform_topology(n, 0.5, 0.3, 0.5, 0.0, 0.0, "adv", seed=8)
+    O.check_ind(mo["Ind"])
+    i, j = (mo["Ind"][:, 0] - 1).astype(int), (mo["Ind"][:, 1] - 1).astype(int)
+    touched = np.zeros(n, bool)
+    touched[i[mo["corrupted"]]] = True
+    touched[j[mo["corrupted"]]] = True
+    assert mo["corrupted"].any() and mo["ErrVec"][~mo["corrupted"]].max() < 1e-7
+    deg = np.bincount(np.concatenate([i, j]), minlength=n)
+    cdeg = np.bincount(np.concatenate([i[mo["corrupted"]], j[mo["corrupted"]]]), minlength=n)
+    heavy = cdeg >= np.floor(0.5 * deg)                               # the corrupted nodes
+    assert heavy.sum() >= int(np.floor(n * 0.3))
