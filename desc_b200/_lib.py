@@ -26,7 +26,7 @@ SYMBOLS = [
     "desc_b200_get_incidence", "desc_b200_get_slots", "desc_b200_get_s0", "desc_b200_get_w",
     "desc_b200_get_gcw_info", "desc_b200_get_timings", "desc_b200_sync",
     "desc_b200_cemp", "desc_b200_cemp_gcw", "desc_b200_cycle_reweight", "desc_b200_rotation_alignment",
-    "desc_b200_pgd_diag",
+    "desc_b200_pgd_diag", "desc_b200_mst_init", "desc_b200_mpls_refine",
     "desc_b200_generate", "desc_b200_model_destroy", "desc_b200_model_info", "desc_b200_model_fetch",
     "desc_b200_model_device",
 ]
@@ -52,6 +52,12 @@ class GenOpts(C.Structure):
                 ("p_edge_crpt", C.c_double), ("seed", C.c_uint64)]
 
 
+class MplsParams(C.Structure):
+    _fields_ = [("stop_threshold", C.c_double), ("max_iter", C.c_int32), ("n_reweighting", C.c_int32),
+                ("n_thresholding", C.c_int32), ("n_cycle_info_ratio", C.c_int32), ("reweighting", C.c_void_p),
+                ("thresholding", C.c_void_p), ("cycle_info_ratio", C.c_void_p)]
+
+
 class StepRule(C.Structure):
     _fields_ = [("kind", C.c_int32), ("strategy", C.c_int32), ("lr", C.c_double), ("decay_interval", C.c_double),
                 ("beta_1", C.c_double), ("beta_2", C.c_double), ("t", C.c_int64)]
@@ -63,7 +69,8 @@ class Timings(C.Structure):
                 ("pgd_launches", C.c_int32), ("gcw_iters", C.c_int32), ("total_launches", C.c_int32),
                 ("reserved", C.c_int32), ("pgd_pass1_ms", C.c_double), ("pgd_pass2_ms", C.c_double),
                 ("pgd_comm_ms", C.c_double), ("laa_ms", C.c_double), ("laa_iters", C.c_int32), ("laa_cg_iters", C.c_int32),
-                ("cemp_ms", C.c_double), ("cemp_iters", C.c_int32), ("reserved2", C.c_int32)]
+                ("cemp_ms", C.c_double), ("cemp_iters", C.c_int32), ("reserved2", C.c_int32),
+                ("mst_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
@@ -112,6 +119,8 @@ def load():
     lib.desc_b200_model_info.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_double)]
     lib.desc_b200_model_fetch.argtypes = [vp, dp, dp, dp, dp, dp, vp]
     lib.desc_b200_model_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.desc_b200_mst_init.argtypes = [vp, dp, dp]
+    lib.desc_b200_mpls_refine.argtypes = [vp, dp, dp, C.POINTER(MplsParams), dp, C.POINTER(i32), dp]
     lib.desc_b200_cemp.argtypes = [vp, i32, dp, i32, dp]
     lib.desc_b200_cemp_gcw.argtypes = [vp, dp, dp]
     lib.desc_b200_cycle_reweight.argtypes = [vp, dp, C.c_double, C.c_double, dp]

@@ -5,6 +5,7 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <cmath>
 
 static thread_local char g_err[1024] = "";
 
@@ -72,7 +73,7 @@ void desc_b200_destroy(desc_b200_handle* h) {
                     h->d_ctrl_f, h->omega, h->isd, h->X[0], h->X[1], h->gcw_coef, h->gcw_red,
                     h->gcw_small, h->gcw_res, h->R_est, h->d_err, h->d_Sin, h->rk_i, h->rk_j, h->estart,
                     h->pgd_partial, h->jhdr, h->sjk, h->thr_key, h->thr_k, h->comm_scratch,
-                    h->cemp_S[0], h->cemp_S[1], h->diag_work, h->diag_hist};
+                    h->cemp_S[0], h->cemp_S[1], h->diag_work, h->diag_hist, h->R_mst};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
@@ -388,6 +389,106 @@ int desc_b200_cycle_reweight(desc_b200_handle* h, const double* x, double beta, 
         desc_set_error("CUDA error %s in cycle_reweight", cudaGetErrorString(e));
         return DESC_B200_ERR_CUDA;
     }
+    h->tm.total_launches = h->launches;
+    return rc;
+}
+
+// MPLS.m:152-195: CEMP+MST initialisation
+int desc_b200_mst_init(desc_b200_handle* h, const double* SVec, double* R_out) {
+    DESC_TRY(check_handle(h));
+    const double* d_S = nullptr;
+    if (SVec) {
+        if (!h->d_Sin) CUDA_TRY(cudaMalloc(&h->d_Sin, h->m * sizeof(double)));
+        CUDA_TRY(cudaMemcpyAsync(h->d_Sin, SVec, h->m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        d_S = h->d_Sin;
+    } else {
+        if (!h->have_cemp) {
+            desc_set_error("mst_init with SVec=NULL needs a previous cemp on this handle");
+            return DESC_B200_ERR_STATE;
+        }
+        d_S = h->cemp_S[h->cemp_final];
+    }
+    if (!h->R_mst) CUDA_TRY(cudaMalloc(&h->R_mst, 9 * (size_t)h->n * sizeof(double)));
+    h->have_mst = false;
+    {
+        StageTimer t(h, &h->tm.mst_ms);
+        DESC_TRY(desc_mst_init_impl(h, d_S, h->R_mst));
+        DESC_TRY(t.stop());
+    }
+    h->have_mst = true;
+    if (R_out) {
+        CUDA_TRY(cudaMemcpyAsync(R_out, h->R_mst, 9 * (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    h->tm.total_launches = h->launches;
+    return DESC_B200_OK;
+}
+
+// MPLS.m:198-256: the reweighting loop
+int desc_b200_mpls_refine(desc_b200_handle* h, const double* SVec, const double* R_init,
+                          const desc_b200_mpls_params* p, double* R_out, int32_t* iters_run, double* scores) {
+    DESC_TRY(check_handle(h));
+    if (!p || p->max_iter < 1 || !p->reweighting || !p->thresholding || !p->cycle_info_ratio || p->n_reweighting < 1 ||
+        p->n_thresholding < 1 || p->n_cycle_info_ratio < 1) {
+        desc_set_error("mpls_refine: MPLS_parameters need max_iter >= 1 and non-empty reweighting / thresholding / "
+                       "cycle_info_ratio");
+        return DESC_B200_ERR_ARG;
+    }
+    if (!h->have_s0) {
+        desc_set_error("mpls_refine before cycle_inconsistency");
+        return DESC_B200_ERR_STATE;
+    }
+    const double* d_S = nullptr;
+    if (SVec) {
+        if (!h->d_Sin) CUDA_TRY(cudaMalloc(&h->d_Sin, h->m * sizeof(double)));
+        CUDA_TRY(cudaMemcpyAsync(h->d_Sin, SVec, h->m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        d_S = h->d_Sin;
+    } else {
+        if (!h->have_cemp) {
+            desc_set_error("mpls_refine with SVec=NULL needs a previous cemp on this handle");
+            return DESC_B200_ERR_STATE;
+        }
+        d_S = h->cemp_S[h->cemp_final];
+    }
+    if (!R_init && !h->have_mst) {
+        desc_set_error("mpls_refine with R_init=NULL needs a previous mst_init on this handle");
+        return DESC_B200_ERR_STATE;
+    }
+    // MPLS.m:43-63: short parameter vectors are padded with their last element
+    const int len = p->max_iter;
+    std::vector<double> beta(len), tau(len), alpha(len);
+    for (int t = 0; t < len; t++) {
+        beta[t] = p->reweighting[std::min(t, p->n_reweighting - 1)];
+        tau[t] = p->thresholding[std::min(t, p->n_thresholding - 1)];
+        alpha[t] = p->cycle_info_ratio[std::min(t, p->n_cycle_info_ratio - 1)];
+    }
+    desc_laa_sched sched = {beta.data(), tau.data(), alpha.data(), len, std::acos(-0.5) / 3.14159265358979323846};
+    double *d_R = nullptr, *d_out = nullptr;
+    const size_t n9 = 9 * (size_t)h->n;
+    CUDA_TRY(cudaMalloc(&d_out, n9 * sizeof(double)));
+    if (R_init) {
+        CUDA_TRY(cudaMalloc(&d_R, n9 * sizeof(double)));
+        CUDA_TRY(cudaMemcpyAsync(d_R, R_init, n9 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    int run = 0, rc;
+    {
+        StageTimer t(h, &h->tm.laa_ms);
+        rc = desc_laa_impl(h, d_S, d_R ? d_R : h->R_mst, d_out, p->max_iter, p->stop_threshold, &run, scores, &sched);
+        if (rc == DESC_B200_OK) rc = t.stop();
+    }
+    if (rc == DESC_B200_OK && R_out) {
+        cudaError_t e = cudaMemcpyAsync(R_out, d_out, n9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) {
+            desc_set_error("CUDA error %s copying the MPLS rotations", cudaGetErrorString(e));
+            rc = DESC_B200_ERR_CUDA;
+        }
+    }
+    cudaFree(d_out);
+    if (d_R) cudaFree(d_R);
+    if (iters_run) *iters_run = run;
+    h->tm.laa_iters = run;
+    h->tm.laa_cg_iters = h->laa_cg_iters;
     h->tm.total_launches = h->launches;
     return rc;
 }

@@ -152,6 +152,8 @@ struct desc_b200_handle {
     double* cemp_S[2] = {nullptr, nullptr};  // m each (ping-pong)
     int cemp_final = 0;
     bool have_cemp = false;
+    double* R_mst = nullptr;    // 9n: CEMP+MST rotations of the last mst_init
+    bool have_mst = false;
 
     // make_plots diagnostics (diag.cu): per-iteration S_vec error, GCW, alignment (DESC.m:235-239)
     bool diag_on = false;
@@ -175,8 +177,18 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample, uint64_t seed,
 int desc_cycle_impl(desc_b200_handle* h);
 int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int* iters_run);
 int desc_gcw_impl(desc_b200_handle* h, const double* d_S);
+// per-iteration parameters of the MPLS loop (MPLS.m:39-63), padded to `len` by the caller; nullptr = DESC.m:265-312
+struct desc_laa_sched {
+    const double* beta;    // reweighting
+    const double* tau;     // thresholding
+    const double* alpha;   // cycle_info_ratio
+    int len;
+    double empty_value;    // HVec of edges without a 3-cycle: acos(-1/2)/pi (zero R_cycle, MPLS.m:125-135)
+};
 int desc_laa_impl(desc_b200_handle* h, const double* d_S, const double* d_Rinit, double* d_Rout, int max_iters,
-                  double stop_threshold, int* iters_run, double* scores_host);
+                  double stop_threshold, int* iters_run, double* scores_host, const desc_laa_sched* mpls = nullptr);
+// MPLS.m:152-195: minimum spanning tree of SVec+1 and rotations multiplied along it from node 1 (mpls.cu)
+int desc_mst_init_impl(desc_b200_handle* h, const double* d_S, double* d_R);
 int desc_cemp_impl(desc_b200_handle* h, int max_iter, const double* beta, int n_beta);
 int desc_cemp_reweight(desc_b200_handle* h, const double* x_cur, double* x_next, double beta, double empty_value);
 // Rotation_Alignment.m on the device: out[0]=mean error, out[1]=median error (degrees), out[2..10]=R_align;

@@ -309,6 +309,16 @@ __global__ void k_laa_edge_update(const int* __restrict__ ei, const int* __restr
     const double w = 1.0 / pow(rs, 0.75);
     W[e] = w > wmax ? wmax : w;
 }
+// MPLS.m:241-242: RHVec = (1-alpha) ResVec + alpha HVec (in place in RS), Weights = min(RHVec^-0.75, wmax)
+__global__ void k_laa_mix(const double* __restrict__ H, int64_t m, double alpha, double wmax, double* __restrict__ RS,
+                          double* __restrict__ W) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= m) return;
+    const double rs = (1.0 - alpha) * RS[e] + alpha * H[e];
+    RS[e] = rs;
+    const double w = 1.0 / pow(rs, 0.75);
+    W[e] = w > wmax ? wmax : w;
+}
 __global__ void k_laa_truncate(const double* __restrict__ RS, int64_t m, double thresh, double wmin, double* __restrict__ W) {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= m) return;
@@ -417,7 +427,7 @@ static int laa_quantile(desc_b200_handle* h, const double* X, int64_t m, double 
 }
 
 int desc_laa_impl(desc_b200_handle* h, const double* d_S, const double* d_Rinit, double* d_Rout, int max_iters,
-                  double stop_threshold, int* iters_run, double* scores_host) {
+                  double stop_threshold, int* iters_run, double* scores_host, const desc_laa_sched* mpls) {
     if (h->world > 1) {
         desc_set_error("desc_b200_refine: the LAA refinement runs on one GPU (call it on a world==1 handle)");
         return DESC_B200_ERR_STATE;
@@ -445,9 +455,12 @@ int desc_laa_impl(desc_b200_handle* h, const double* d_S, const double* d_Rinit,
     CUDA_TRY(cudaMalloc(&partial, (size_t)3 * LAA_RED_BLOCKS * sizeof(double)));
     CUDA_TRY(cudaMalloc(&sc, 32 * sizeof(double)));
     CUDA_TRY(cudaMalloc(&d_hist, 2048 * sizeof(unsigned)));
-    void* to_free[] = {Q, QQ, W, B, RS, w2adj, rhs, diag, X, R, Z, P, AP, Wq, partial, sc, d_hist};
+    double* H = nullptr;   // MPLS: cycle-reweighted residuals (HVec)
+    if (mpls) CUDA_TRY(cudaMalloc(&H, (size_t)m * sizeof(double)));
+    void* to_free[] = {Q, QQ, W, B, RS, w2adj, rhs, diag, X, R, Z, P, AP, Wq, partial, sc, d_hist, H};
     auto cleanup = [&]() {
-        for (void* p : to_free) cudaFree(p);
+        for (void* p : to_free)
+            if (p) cudaFree(p);
     };
     const unsigned gm = (unsigned)((m + LAA_TB - 1) / LAA_TB), gn = (unsigned)((n + LAA_TB - 1) / LAA_TB);
     const unsigned gw = (unsigned)(((int64_t)n * 32 + LAA_TB - 1) / LAA_TB);
@@ -514,11 +527,21 @@ int desc_laa_impl(desc_b200_handle* h, const double* d_S, const double* d_Rinit,
         KERNEL_CHECK(h);
         CUDA_TRY(cudaMemcpyAsync(&score, sc + 15, sizeof(double), cudaMemcpyDeviceToHost, st));
         // ---- edge residuals, new weights, quantile truncation
-        k_laa_edge_update<<<gm, LAA_TB, 0, st>>>(h->ei, h->ej, Wq, B, d_S, m, lam, wmax, RS, W);
+        k_laa_edge_update<<<gm, LAA_TB, 0, st>>>(h->ei, h->ej, Wq, B, d_S, m, mpls ? 0.0 : lam, wmax, RS, W);
         KERNEL_CHECK(h);
-        quant_ratio = std::max(qmin, quant_ratio - 0.05);
         double thresh = 0.0;
-        rc = laa_quantile(h, RS, m, quant_ratio, d_hist, &thresh);   // (synchronises: score is valid after it)
+        if (mpls) {
+            // MPLS.m:224-244: RS holds ResVec (lam = 0); HVec = cycle reweighting of the residuals, convex mix, quantile
+            const int idx = std::min(it - 1, mpls->len - 1);
+            rc = desc_cemp_reweight(h, RS, H, mpls->beta[idx], mpls->empty_value);
+            if (rc != DESC_B200_OK) break;
+            k_laa_mix<<<gm, LAA_TB, 0, st>>>(H, m, mpls->alpha[idx], wmax, RS, W);
+            KERNEL_CHECK(h);
+            rc = laa_quantile(h, RS, m, mpls->tau[idx], d_hist, &thresh);
+        } else {
+            quant_ratio = std::max(qmin, quant_ratio - 0.05);
+            rc = laa_quantile(h, RS, m, quant_ratio, d_hist, &thresh);   // (synchronises: score is valid after it)
+        }
         if (rc != DESC_B200_OK) break;
         k_laa_truncate<<<gm, LAA_TB, 0, st>>>(RS, m, thresh, wmin, W);
         KERNEL_CHECK(h);

@@ -10,6 +10,7 @@ Function names, argument meaning and outputs follow the reference's MATLAB funct
 
 * ``CEMP(Ind, RijMat, CEMP_parameters) -> SVec``          Algorithms/CEMP.m:25      
 * ``CEMP_GCW(Ind, RijMat, CEMP_parameters) -> R_est``     Algorithms/CEMP_GCW.m:25
+* ``MPLS(Ind, RijMat, CEMP_parameters, MPLS_parameters) -> (R_est, R_init)``   Algorithms/MPLS.m:28
 * ``Rotation_Alignment(R_est, R_gt) -> (R_out, R_align, mean_error, median_error)``  Utils/Rotation_Alignment.m:13
 
 ``Ind`` is the reference's m x 2, 1-based, i<j, (i,j)-sorted edge list; ``RijMat`` is
@@ -246,6 +247,42 @@ class Solver:
         R = np.empty((3, 3, self.info()["n"]), dtype=np.float64, order="F")
         _lib.check(self._lib.desc_b200_cemp_gcw(self._h, _ptr(S), _ptr(R)))
         return R
+
+    def mst_init(self, SVec=None):
+        """MPLS.m:152-195: rotations multiplied along the minimum spanning tree of SVec+1 -> R 3x3xn (CEMP+MST)."""
+        S = None if SVec is None else np.ascontiguousarray(np.asarray(SVec, dtype=np.float64).ravel())
+        if S is not None and S.size != self.m:
+            raise ValueError("SVec must have m entries")
+        R = np.empty((3, 3, self.info()["n"]), dtype=np.float64, order="F")
+        _lib.check(self._lib.desc_b200_mst_init(self._h, _ptr(S), _ptr(R)))
+        return R
+
+    def mpls_refine(self, MPLS_parameters, SVec=None, R_init=None):
+        """MPLS.m:198-256 -> (R_est 3x3xn, scores).  Defaults: SVec of the last cemp, R_init of the last mst_init."""
+        n = self.info()["n"]
+        S = None if SVec is None else np.ascontiguousarray(np.asarray(SVec, dtype=np.float64).ravel())
+        if S is not None and S.size != self.m:
+            raise ValueError("SVec must have m entries")
+        R0 = None
+        if R_init is not None:
+            R0 = np.asfortranarray(np.asarray(R_init, dtype=np.float64))
+            if R0.shape != (3, 3, n):
+                raise ValueError("R_init must be 3 x 3 x n")
+        vecs = [np.ascontiguousarray(np.asarray(_param(MPLS_parameters, k), dtype=np.float64).ravel())
+                for k in ("reweighting", "thresholding", "cycle_info_ratio")]
+        if any(v.size == 0 for v in vecs):
+            raise ValueError("MPLS_parameters.reweighting / thresholding / cycle_info_ratio must not be empty")
+        max_iter = int(_param(MPLS_parameters, "max_iter"))
+        p = _lib.MplsParams(stop_threshold=float(_param(MPLS_parameters, "stop_threshold")), max_iter=max_iter,
+                            n_reweighting=vecs[0].size, n_thresholding=vecs[1].size, n_cycle_info_ratio=vecs[2].size,
+                            reweighting=vecs[0].ctypes.data, thresholding=vecs[1].ctypes.data,
+                            cycle_info_ratio=vecs[2].ctypes.data)
+        R = np.empty((3, 3, n), dtype=np.float64, order="F")
+        scores = np.zeros(max(max_iter, 1), dtype=np.float64)
+        run = C.c_int32(0)
+        _lib.check(self._lib.desc_b200_mpls_refine(self._h, _ptr(S), _ptr(R0), C.byref(p), _ptr(R), C.byref(run),
+                                                  _ptr(scores)))
+        return R, scores[:run.value].copy()
 
     def cycle_reweight(self, x, beta, empty_value=1.0):
         """One cycle reweighting of an edge vector (CEMP.m:109-125; HVec of MPLS.m:219-233)."""
@@ -513,6 +550,32 @@ def CEMP(Ind, RijMat, CEMP_parameters, **solver_kw):
 def CEMP_GCW(Ind, RijMat, CEMP_parameters, **solver_kw):
     """``R_est = CEMP_GCW(Ind, RijMat, CEMP_parameters)`` (Algorithms/CEMP_GCW.m:25)."""
     return _run_cemp(Ind, RijMat, CEMP_parameters, True, **solver_kw)[1]
+
+
+def MPLS(Ind, RijMat, CEMP_parameters, MPLS_parameters, **solver_kw):
+    """``[R_est, R_init] = MPLS(Ind, RijMat, CEMP_parameters, MPLS_parameters)`` (Algorithms/MPLS.m:28): CEMP
+    (:66-150), CEMP+MST initialisation (:152-195) and the MPLS reweighting loop (:198-256), all on the device."""
+    verbose = _param(MPLS_parameters, "verbose", False)
+    s = Solver(Ind, RijMat, **solver_kw)
+    try:
+        s.build_incidence(n_sample=int(_param(CEMP_parameters, "nsample")), seed=int(_param(CEMP_parameters, "seed", 0) or 0),
+                          cycles=_param(CEMP_parameters, "cycles"))
+        s.cycle_inconsistency()
+        s.cemp(int(_param(CEMP_parameters, "max_iter")), _param(CEMP_parameters, "reweighting"))
+        if verbose:
+            print("Building minimum spanning tree ...")          # MPLS.m:153
+        R_init = s.mst_init()
+        if verbose:
+            print("Rotation Initialized!")                       # MPLS.m:216
+            print("Start MPLS reweighting ...")
+        R_est, scores = s.mpls_refine(MPLS_parameters)
+        if verbose:
+            for t, sc in enumerate(scores):                      # MPLS.m:248
+                print("Iter %d: ||\u0394R||= %f" % (t + 1, sc))
+            print("DONE!")
+    finally:
+        s.close()
+    return R_est, R_init
 
 
 def Rotation_Alignment(R_est, R_gt, **solver_kw):

@@ -103,6 +103,7 @@ typedef struct desc_b200_timings {
     double cemp_ms;       /* cemp: initial mean + all reweighting iterations                  */
     int32_t cemp_iters;   /* reweighting iterations of the last cemp call                     */
     int32_t reserved2;
+    double mst_ms;        /* mst_init: spanning tree + propagation                            */
 } desc_b200_timings;
 
 const char* desc_b200_last_error(void);
@@ -198,6 +199,27 @@ int desc_b200_cemp_gcw(desc_b200_handle* h, const double* SVec, double* R_out);
    w_s = exp(-beta (x(e_ki)+x(e_jk))); edges without cycles get empty_value.  This is CEMP.m:109-125
    (empty_value 1) and the HVec step of MPLS.m:219-233 with x = ResVec.                                */
 int desc_b200_cycle_reweight(desc_b200_handle* h, const double* x, double beta, double empty_value, double* out);
+/* MPLS (Algorithms/MPLS.m:28) = cemp + mst_init + mpls_refine.
+   mst_init (MPLS.m:152-195): minimum spanning tree of the graph weighted by SVec+1 (ties broken by the edge index),
+   R_1 = I, rotations multiplied along the tree -- the CEMP+MST estimate the demo reports (compare_algorithms.m:77).
+   SVec = NULL: the last cemp.  DESC_B200_ERR_ARG if the graph is not connected.  One GPU.                    */
+int desc_b200_mst_init(desc_b200_handle* h, const double* SVec, double* R_out);
+typedef struct desc_b200_mpls_params {
+    double stop_threshold;            /* MPLS_parameters.stop_threshold                               */
+    int32_t max_iter;                 /* MPLS_parameters.max_iter                                     */
+    int32_t n_reweighting;            /* lengths of the three vectors below; short vectors are padded */
+    int32_t n_thresholding;           /* with their last element (MPLS.m:43-63)                       */
+    int32_t n_cycle_info_ratio;
+    const double* reweighting;        /* beta_t                                                       */
+    const double* thresholding;       /* tau_t: quantile above which an edge weight drops to 1e-4     */
+    const double* cycle_info_ratio;   /* alpha_t: weight of the cycle information hij vs the residual */
+} desc_b200_mpls_params;
+/* mpls_refine (MPLS.m:198-256): Weighted_LAA step, residuals r_ij, h_ij = cycle reweighting of the residuals
+   (needs build_incidence + cycle_inconsistency), weights (alpha h + (1-alpha) r)^-0.75 capped at 1e4, edges above the
+   tau-quantile set to 1e-4; stops at score <= stop_threshold or max_iter-1 iterations.  SVec = NULL: the last
+   cemp (initial weights); R_init = NULL: the last mst_init.  scores (may be NULL): max_iter doubles.  One GPU. */
+int desc_b200_mpls_refine(desc_b200_handle* h, const double* SVec, const double* R_init,
+                          const desc_b200_mpls_params* params, double* R_out, int32_t* iters_run, double* scores);
 
 /* ---- evaluation / diagnostics ----
    Utils/Rotation_Alignment.m:13-38 (== GlobalSOdCorrectRight.m): R_est, R_gt 3x3xn (n of the handle);

@@ -878,3 +878,116 @@ def pgd_diagnostics(Ind, RijMat, S_hist, ErrVec, R_orig):
         _, _, mean_err, med_err = rotation_alignment(R, R_orig)
         out[t] = [float(np.mean(np.abs(ErrVec - S))), mean_err, med_err]
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# MPLS on the same incidence (Algorithms/MPLS.m)
+# --------------------------------------------------------------------------------------------
+def _pad(v, length):
+    """MPLS.m:43-63: a short parameter vector is padded with its last element."""
+    v = [float(x) for x in np.asarray(v, dtype=np.float64).ravel()]
+    return v + [v[-1]] * max(0, length - len(v))
+
+
+def mst_init(Ind, RijMat, SVec):
+    """MPLS.m:152-195: minimum spanning tree of the graph weighted by SVec+1, then R_i by multiplying Rij along
+    the tree from node 1 (R_1 = I).  ``minspantree``'s tie-breaking is not documented; here (and on the device) ties
+    are broken by the edge index, i.e. the tree is the unique MST under the total order (weight, edge id)."""
+    n, ei, ej = check_ind(Ind)
+    R = to_internal(RijMat)
+    w = np.asarray(SVec, dtype=np.float64).ravel() + 1.0                          # :154
+    order = np.lexsort((np.arange(ei.size), w))                                   # Kruskal on (weight, edge id)
+    parent = np.arange(n)
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    tree = []
+    for e in order:
+        a, b = find(int(ei[e])), find(int(ej[e]))
+        if a != b:
+            parent[a] = b
+            tree.append(int(e))
+            if len(tree) == n - 1:
+                break
+    if len(tree) != n - 1:
+        raise ValueError("graph is not connected (the reference's loop MPLS.m:171 would not terminate)")
+    nbr = [[] for _ in range(n)]
+    for e in tree:
+        nbr[int(ei[e])].append((int(ej[e]), e))
+        nbr[int(ej[e])].append((int(ei[e]), e))
+    R_est = np.zeros((n, 3, 3))
+    R_est[0] = np.eye(3)                                                          # :165-167
+    added = np.zeros(n, bool)
+    added[0] = True
+    roots = [0]
+    while roots:                                                                  # :171-186
+        new = []
+        for r in roots:
+            for leaf, e in nbr[r]:
+                if added[leaf]:
+                    continue
+                # edge_leaf = IndMat(leaf, root) > 0 <=> leaf < root: R_leaf = Rij * R_root, else Rij' * R_root
+                R_est[leaf] = (R[e] if leaf < r else R[e].T) @ R_est[r]
+                added[leaf] = True
+                new.append(leaf)
+        roots = new
+    return to_matlab(R_est), np.array(sorted(tree), dtype=np.int64)
+
+
+def mpls_refine(Ind, RijMat, inc: Incidence, S0, SVec, R_init, MPLS_parameters, weight_max=1e4, weight_min=1e-4,
+                return_info=False):
+    """MPLS.m:198-256: the reweighting loop (Weighted_LAA + cycle reweighting of the residuals)."""
+    n, ei, ej = check_ind(Ind)
+    stop_threshold = float(MPLS_parameters["stop_threshold"])
+    maxIters = int(MPLS_parameters["max_iter"])
+    beta = _pad(MPLS_parameters["reweighting"], maxIters)                         # :43-47
+    tau = _pad(MPLS_parameters["thresholding"], maxIters)                         # :49-53
+    alpha = _pad(MPLS_parameters["cycle_info_ratio"], maxIters)                   # :55-59
+    S = np.asarray(SVec, dtype=np.float64).ravel()
+    RR = np.transpose(np.asarray(RijMat, dtype=np.float64), (1, 0, 2))            # :201
+    A = build_amatrix(ei, ej, n)
+    Q = R2Q(np.asarray(R_init, dtype=np.float64))
+    QQ = R2Q(RR)
+    score, it = math.inf, 1
+    with np.errstate(divide="ignore"):
+        Weights = 1.0 / S ** 0.75                                                 # :211
+    Weights[Weights > weight_max] = weight_max                                    # :214
+    # S0Mat columns of edges without a cycle are acos(-1/2)/pi (R_cycle = 0, MPLS.m:125-135): HVec = 2/3 there
+    empty = float(np.arccos(-0.5) / np.pi)
+    scores = []
+    while score > stop_threshold and it < maxIters:                              # :219
+        Q, W, B, score = weighted_laa(ei, ej, Q, QQ, A, Weights)
+        E = A @ W[1:, 1:4] - B                                                    # :222
+        ResVec = np.sqrt(np.sum(E * E, axis=1)) / math.pi
+        HVec = cemp_reweight(inc, S0, ResVec, beta[it - 1], empty_value=empty)    # :224-238
+        RHVec = (1.0 - alpha[it - 1]) * ResVec + alpha[it - 1] * HVec             # :241
+        with np.errstate(divide="ignore"):
+            Weights = 1.0 / RHVec ** 0.75                                         # :242
+        thresh = matlab_quantile(RHVec, tau[it - 1])                              # :244
+        Weights[Weights > weight_max] = weight_max
+        Weights[RHVec > thresh] = weight_min
+        scores.append(score)
+        it += 1
+    R_est = np.zeros((3, 3, n))
+    for i in range(n):
+        R_est[:, :, i] = q2R(Q[i])
+    if return_info:
+        return R_est, dict(scores=np.array(scores), iterations=it - 1)
+    return R_est
+
+
+def MPLS(Ind, RijMat, CEMP_parameters, MPLS_parameters, seed=0, cycles=None, return_info=False):
+    """``[R_est, R_init] = MPLS(Ind, RijMat, CEMP_parameters, MPLS_parameters)`` (Algorithms/MPLS.m:28)."""
+    inc = cemp_incidence(Ind, CEMP_parameters["nsample"], seed=seed, cycles=cycles)
+    S0 = cycle_inconsistency(inc, RijMat)
+    SVec = cemp(inc, S0, CEMP_parameters["max_iter"], CEMP_parameters["reweighting"])
+    R_init, tree = mst_init(Ind, RijMat, SVec)
+    R_est, info = mpls_refine(Ind, RijMat, inc, S0, SVec, R_init, MPLS_parameters, return_info=True)
+    if return_info:
+        info.update(SVec=SVec, tree=tree)
+        return R_est, R_init, info
+    return R_est, R_init

@@ -17,8 +17,9 @@ statement-by-statement restatement of the loop and of Utils/Weighted_LAA.m).
 
 ``cemp_*.npz`` hold a with-replacement draw ``CoIndMat`` standing in for CEMP.m:63 (MATLAB's
 ``datasample`` stream cannot be restated, so the draw is part of the fixture), the literal CEMP.m / CEMP_GCW.m
-outputs on it (``S0Mat``, ``SVec`` after every reweighting, ``R_est``) and the alignment metric
-(Utils/Rotation_Alignment.m) of ``R_est`` against ``R_orig``.  A MATLAB user can replay them by replacing the
+outputs on it (``S0Mat``, ``SVec`` after every reweighting, ``R_est``), the alignment metric
+(Utils/Rotation_Alignment.m) of ``R_est`` against ``R_orig``, and the MPLS.m:152-256 stages on the same draw
+(``R_mst``, ``mst_edges``, ``R_mpls``, ``mpls_scores`` with the demo's MPLS_parameters).  A MATLAB user can replay them by replacing the
 ``datasample`` call with the stored ``CoIndMat`` column.
 
     python tests/golden/make_golden.py            # everything
@@ -71,7 +72,18 @@ def make_cemp(prefix):
         Co, ptr, apex = cemp_draw(mo["Ind"], P["nsample"], dseed)
         SVec, ex = cemp_literal(mo["Ind"], mo["RijMat"], P, Co, return_gcw=True)
         _, R_align, mean_err, med_err = O.rotation_alignment(ex["R_est"], mo["R_orig"])
-        out = dict(Ind=mo["Ind"], RijMat=mo["RijMat"], R_orig=mo["R_orig"], ErrVec=mo["ErrVec"],
+        # MPLS.m:152-256 on the same draw and the literal SVec (oracle.mst_init / mpls_refine)
+        MP = dict(stop_threshold=1e-3, max_iter=100, reweighting=[P["reweighting"][-1]],
+                  thresholding=[0.95, 0.9, 0.85, 0.8], cycle_info_ratio=1.0 / (np.arange(1, 101) + 1))   # compare_algorithms.m:36-40
+        inc = O.cemp_incidence(mo["Ind"], cycles=(ptr, apex))
+        S0 = O.cycle_inconsistency(inc, mo["RijMat"])
+        R_mst, tree = O.mst_init(mo["Ind"], mo["RijMat"], SVec)
+        R_mpls, mi = O.mpls_refine(mo["Ind"], mo["RijMat"], inc, S0, SVec, R_mst, MP, return_info=True)
+        out = dict(R_mst=R_mst, mst_edges=tree + 1, R_mpls=R_mpls, mpls_scores=mi["scores"],
+                   mpls_stop_threshold=np.float64(MP["stop_threshold"]), mpls_max_iter=np.int64(MP["max_iter"]),
+                   mpls_reweighting=np.array(MP["reweighting"]), mpls_thresholding=np.array(MP["thresholding"]),
+                   mpls_cycle_info_ratio=np.array(MP["cycle_info_ratio"]))
+        out.update(Ind=mo["Ind"], RijMat=mo["RijMat"], R_orig=mo["R_orig"], ErrVec=mo["ErrVec"],
                    max_iter=np.int64(P["max_iter"]), reweighting=np.array(P["reweighting"], dtype=np.float64),
                    nsample=np.int64(P["nsample"]), CoIndMat=Co, cyc_ptr=ptr, cyc_apex=apex, S0Mat=ex["S0Mat"],
                    SVec=SVec, SVec_hist=np.array(ex["hist"]), R_est=ex["R_est"], R_align=R_align,

@@ -312,3 +312,30 @@ def test_pgd_diagnostics_follow_the_iterates():
     assert d[-1, 0] == pytest.approx(np.mean(np.abs(mo["ErrVec"] - S_vec)))
     R = O.gcw(mo["Ind"], mo["RijMat"], S_vec)
     assert d[-1, 1] == pytest.approx(O.rotation_alignment(R, mo["R_orig"])[2])
+
+
+def test_mst_init_and_mpls_known_answers():
+    """MPLS.m:152-256 restatement: the tree is a minimum spanning tree, clean data is reproduced exactly, the
+    refinement improves on the CEMP+MST initialisation"""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import minimum_spanning_tree
+    mo = O.uniform_topology(70, 0.4, 0.2, 0.1, "uniform", rng=12)
+    n, ei, ej = O.check_ind(mo["Ind"])
+    CP = dict(max_iter=6, reweighting=2.0 ** np.arange(6), nsample=30)
+    MP = dict(stop_threshold=1e-3, max_iter=100, reweighting=[32.0], thresholding=[0.95, 0.9, 0.85, 0.8],
+              cycle_info_ratio=1.0 / (np.arange(1, 101) + 1))
+    R, R0, info = O.MPLS(mo["Ind"], mo["RijMat"], CP, MP, seed=1, return_info=True)
+    w = info["SVec"] + 1.0
+    T = minimum_spanning_tree(sp.coo_matrix((w, (ei, ej)), shape=(n, n)).tocsr())
+    assert info["tree"].size == n - 1 and abs(T.sum() - w[info["tree"]].sum()) < 1e-9
+    e_init = O.rotation_alignment(R0, mo["R_orig"])[2]
+    e_mpls = O.rotation_alignment(R, mo["R_orig"])[2]
+    assert 1 <= info["iterations"] < 99 and info["scores"][-1] <= 1e-3 and e_mpls < e_init and e_mpls < 3.0
+    # clean graph: rotations along any tree are exact, the loop stops immediately
+    mo = O.uniform_topology(40, 0.4, 0.0, 0.0, rng=13)
+    R, R0, info = O.MPLS(mo["Ind"], mo["RijMat"], CP, MP, seed=1, return_info=True)
+    assert O.aligned_angle_deg(R0, mo["R_orig"]).max() < 1e-5 and info["iterations"] == 1
+    # a disconnected graph is rejected (the reference would loop forever)
+    Ind = np.array([[1.0, 2.0], [3.0, 4.0]])
+    with pytest.raises(ValueError):
+        O.mst_init(Ind, O.to_matlab(O._rand_rot(2, np.random.default_rng(0))), np.ones(2))
