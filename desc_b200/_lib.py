@@ -26,7 +26,7 @@ SYMBOLS = [
     "desc_b200_get_incidence", "desc_b200_get_slots", "desc_b200_get_s0", "desc_b200_get_w",
     "desc_b200_get_gcw_info", "desc_b200_get_timings", "desc_b200_sync",
     "desc_b200_cemp", "desc_b200_cemp_gcw", "desc_b200_cycle_reweight", "desc_b200_rotation_alignment",
-    "desc_b200_pgd_diag", "desc_b200_mst_init", "desc_b200_mpls_refine",
+    "desc_b200_pgd_diag", "desc_b200_mst_init", "desc_b200_mpls_refine", "desc_b200_spectral",
     "desc_b200_generate", "desc_b200_model_destroy", "desc_b200_model_info", "desc_b200_model_fetch",
     "desc_b200_model_device",
 ]
@@ -119,6 +119,7 @@ def load():
     lib.desc_b200_model_info.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_double)]
     lib.desc_b200_model_fetch.argtypes = [vp, dp, dp, dp, dp, dp, vp]
     lib.desc_b200_model_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.desc_b200_spectral.argtypes = [vp, dp]
     lib.desc_b200_mst_init.argtypes = [vp, dp, dp]
     lib.desc_b200_mpls_refine.argtypes = [vp, dp, dp, C.POINTER(MplsParams), dp, C.POINTER(i32), dp]
     lib.desc_b200_cemp.argtypes = [vp, i32, dp, i32, dp]

@@ -366,6 +366,27 @@ int desc_b200_cemp_gcw(desc_b200_handle* h, const double* SVec, double* R_out) {
     return DESC_B200_OK;
 }
 
+// Spectral.m:15-47
+int desc_b200_spectral(desc_b200_handle* h, double* R_out) {
+    DESC_TRY(check_handle(h));
+    int rc;
+    {
+        StageTimer t(h, &h->tm.gcw_ms);
+        h->gcw_weight_rule = 2;
+        rc = desc_gcw_impl(h, nullptr);
+        h->gcw_weight_rule = 0;
+        if (rc == DESC_B200_OK) rc = t.stop();
+    }
+    DESC_TRY(rc);
+    h->have_gcw = true;
+    if (R_out) {
+        CUDA_TRY(cudaMemcpyAsync(R_out, h->R_est, 9 * (size_t)h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    h->tm.total_launches = h->launches;
+    return DESC_B200_OK;
+}
+
 int desc_b200_cycle_reweight(desc_b200_handle* h, const double* x, double beta, double empty_value, double* out) {
     DESC_TRY(check_handle(h));
     if (!h->have_s0) {

@@ -44,10 +44,17 @@
 #define SM_R 36     // 9: R factor of the last Cholesky-QR (block = Q R)
 #define SM_SIZE 48
 
-// rule 0: GCW.m:20 `1./(S.^(3/2)+1e-8)`;  rule 1: CEMP_GCW.m:141 `1./(S+1e-8)`
-__global__ void k_gcw_weights(const double* __restrict__ S, int64_t m, int rule, double* __restrict__ omega) {
+// rule 0: GCW.m:20 `1./(S.^(3/2)+1e-8)`;  rule 1: CEMP_GCW.m:141 `1./(S+1e-8)`;
+// rule 2: Spectral.m:36-40 -- the unweighted, un-normalised block matrix (S unused).  Its eigenvectors are those of
+// Rij_blk/c for any c > 0; c = max degree keeps the spectrum inside [-1,1] like the normalised rules.
+__global__ void k_gcw_weights(const double* __restrict__ S, int64_t m, int rule, double scale, double* __restrict__ omega) {
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (e < m) omega[e] = 1.0 / ((rule == 1 ? S[e] : pow(S[e], 1.5)) + 1e-8);
+    if (e >= m) return;
+    omega[e] = rule == 2 ? scale : 1.0 / ((rule == 1 ? S[e] : pow(S[e], 1.5)) + 1e-8);
+}
+__global__ void k_gcw_unit(double* __restrict__ isd, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) isd[i] = 1.0;
 }
 
 // one warp per node: d_i, isd_i = 1/sqrt(d_i)
@@ -703,9 +710,12 @@ int desc_gcw_impl(desc_b200_handle* h, const double* d_S) {
     const unsigned gbm = (unsigned)((m + 255) / 256);
     CUDA_TRY(cudaMemsetAsync(h->gcw_small, 0, SM_SIZE * sizeof(double), st));
     CUDA_TRY(cudaMemsetAsync(h->gcw_red, 0, 2 * red * sizeof(double), st));
-    k_gcw_weights<<<gbm, 256, 0, st>>>(d_S, m, h->gcw_weight_rule, h->omega);
+    k_gcw_weights<<<gbm, 256, 0, st>>>(d_S, m, h->gcw_weight_rule, 1.0 / (double)std::max(h->maxdeg, 1), h->omega);
     KERNEL_CHECK(h);
-    k_gcw_degree<<<(unsigned)(((int64_t)n * 32 + 255) / 256), 256, 0, st>>>(h->rowstart, h->adj_eid, h->omega, n, h->isd);
+    if (h->gcw_weight_rule == 2)   // Spectral.m: no degree normalisation
+        k_gcw_unit<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->isd, n);
+    else
+        k_gcw_degree<<<(unsigned)(((int64_t)n * 32 + 255) / 256), 256, 0, st>>>(h->rowstart, h->adj_eid, h->omega, n, h->isd);
     KERNEL_CHECK(h);
     k_gcw_coef<<<gbm, 256, 0, st>>>(h->ei, h->ej, h->omega, h->isd, m, h->gcw_coef);
     KERNEL_CHECK(h);

@@ -11,6 +11,7 @@ Function names, argument meaning and outputs follow the reference's MATLAB funct
 * ``CEMP(Ind, RijMat, CEMP_parameters) -> SVec``          Algorithms/CEMP.m:25      
 * ``CEMP_GCW(Ind, RijMat, CEMP_parameters) -> R_est``     Algorithms/CEMP_GCW.m:25
 * ``MPLS(Ind, RijMat, CEMP_parameters, MPLS_parameters) -> (R_est, R_init)``   Algorithms/MPLS.m:28
+* ``Spectral(Ind, RijMat) -> R_est``                      Algorithms/Spectral.m:15
 * ``Rotation_Alignment(R_est, R_gt) -> (R_out, R_align, mean_error, median_error)``  Utils/Rotation_Alignment.m:13
 
 ``Ind`` is the reference's m x 2, 1-based, i<j, (i,j)-sorted edge list; ``RijMat`` is
@@ -246,6 +247,12 @@ class Solver:
             raise ValueError("SVec must have m entries")
         R = np.empty((3, 3, self.info()["n"]), dtype=np.float64, order="F")
         _lib.check(self._lib.desc_b200_cemp_gcw(self._h, _ptr(S), _ptr(R)))
+        return R
+
+    def spectral(self):
+        """Algorithms/Spectral.m:15-47 -> R_est 3x3xn."""
+        R = np.empty((3, 3, self.info()["n"]), dtype=np.float64, order="F")
+        _lib.check(self._lib.desc_b200_spectral(self._h, _ptr(R)))
         return R
 
     def mst_init(self, SVec=None):
@@ -576,6 +583,15 @@ def MPLS(Ind, RijMat, CEMP_parameters, MPLS_parameters, **solver_kw):
     finally:
         s.close()
     return R_est, R_init
+
+
+def Spectral(Ind, RijMat, **solver_kw):
+    """``R_est = Spectral(Ind, RijMat)`` (Algorithms/Spectral.m:15)."""
+    s = Solver(Ind, RijMat, **solver_kw)
+    try:
+        return s.spectral()
+    finally:
+        s.close()
 
 
 def Rotation_Alignment(R_est, R_gt, **solver_kw):

@@ -195,6 +195,9 @@ int desc_b200_cemp(desc_b200_handle* h, int32_t max_iter, const double* reweight
                    double* SVec_out);
 /* CEMP_GCW.m:127-159: GCW with the weights 1./(SVec+1e-8) (:141).  SVec = NULL: the last cemp.       */
 int desc_b200_cemp_gcw(desc_b200_handle* h, const double* SVec, double* R_out);
+/* Algorithms/Spectral.m:15-47: top-3 eigenvectors of the unweighted, un-normalised block matrix of the Rij,
+   projected to SO(3) like GCW.m:28-36 (the `Spectral` row of the demo's table).                          */
+int desc_b200_spectral(desc_b200_handle* h, double* R_out);
 /* One cycle reweighting of an arbitrary edge vector x (m doubles): out(l) = sum_s w_s d_s / sum_s w_s,
    w_s = exp(-beta (x(e_ki)+x(e_jk))); edges without cycles get empty_value.  This is CEMP.m:109-125
    (empty_value 1) and the HVec step of MPLS.m:219-233 with x = ResVec.                                */

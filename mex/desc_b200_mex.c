@@ -7,6 +7,10 @@
  *          [svec_errors, MSE_means, MSE_medians])
  *   out = desc_b200_mex('cemp',  Ind, RijMat, max_iter, reweighting, nsample, seed, want_R)
  *         (Algorithms/CEMP.m / CEMP_GCW.m: out.SVec 1 x m, out.R_est)
+ *   out = desc_b200_mex('mpls',  Ind, RijMat, cemp_max_iter, cemp_reweighting, nsample, seed, stop_threshold,
+ *                       max_iter, reweighting, thresholding, cycle_info_ratio)
+ *         (Algorithms/MPLS.m: out.R_est, out.R_init (CEMP+MST), out.scores)
+ *   R   = desc_b200_mex('spectral', Ind, RijMat)                 (Algorithms/Spectral.m)
  *   out = desc_b200_mex('align', R_est, R_gt)   (Utils/Rotation_Alignment.m: out.R_out, out.R_align,
  *          out.mean_error, out.median_error)
  *   R   = desc_b200_mex('gcw',   Ind, RijMat, S_vec)
@@ -282,6 +286,67 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         plhs[0] = mxCreateStructMatrix(1, 1, 2, fields);
         mxSetField(plhs[0], 0, "SVec", S);
         mxSetField(plhs[0], 0, "R_est", R);
+        return;
+    }
+    if (strcmp(cmd, "mpls") == 0) {
+        if (nrhs != 12) mexErrMsgIdAndTxt("DESC:b200", "mpls: 11 arguments expected");
+        mwSize m;
+        check_inputs(prhs[1], prhs[2], &m);
+        for (int a = 4; a <= 11; a += (a == 4 ? 5 : 1))
+            if (!mxIsDouble(prhs[a]) || mxIsEmpty(prhs[a]))
+                mexErrMsgIdAndTxt("DESC:b200", "reweighting / thresholding / cycle_info_ratio must be non-empty double vectors");
+        const int cemp_iter = (int)mxGetScalar(prhs[3]);
+        const int nsample = (int)mxGetScalar(prhs[5]);
+        const uint64_t seed = (uint64_t)mxGetScalar(prhs[6]);
+        desc_b200_mpls_params P;
+        P.stop_threshold = mxGetScalar(prhs[7]);
+        P.max_iter = (int32_t)mxGetScalar(prhs[8]);
+        P.reweighting = mxGetPr(prhs[9]);
+        P.n_reweighting = (int32_t)mxGetNumberOfElements(prhs[9]);
+        P.thresholding = mxGetPr(prhs[10]);
+        P.n_thresholding = (int32_t)mxGetNumberOfElements(prhs[10]);
+        P.cycle_info_ratio = mxGetPr(prhs[11]);
+        P.n_cycle_info_ratio = (int32_t)mxGetNumberOfElements(prhs[11]);
+        if (nsample <= 0 || P.max_iter < 1) mexErrMsgIdAndTxt("DESC:b200", "nsample and MPLS max_iter must be positive");
+        desc_b200_handle* h = NULL;
+        fail_if(desc_b200_create(&h, 0, (int64_t)m, mxGetPr(prhs[1]), mxGetPr(prhs[2]), NULL), NULL);
+        int64_t info[10];
+        fail_if(desc_b200_get_info(h, info), h);
+        mwSize dims[3] = {3, 3, 0};
+        dims[2] = (mwSize)info[0];
+        mxArray* R = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
+        mxArray* R0 = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
+        mxArray* sc = mxCreateDoubleMatrix(P.max_iter, 1, mxREAL);
+        int32_t run = 0;
+        fail_if(desc_b200_build_incidence(h, nsample, seed, NULL, NULL), h);
+        fail_if(desc_b200_cycle_inconsistency(h), h);
+        fail_if(desc_b200_cemp(h, cemp_iter, mxGetPr(prhs[4]), (int32_t)mxGetNumberOfElements(prhs[4]), NULL), h);
+        fail_if(desc_b200_mst_init(h, NULL, mxGetPr(R0)), h);
+        fail_if(desc_b200_mpls_refine(h, NULL, NULL, &P, mxGetPr(R), &run, mxGetPr(sc)), h);
+        desc_b200_destroy(h);
+        mxArray* scores = mxCreateDoubleMatrix(run, 1, mxREAL);
+        for (int t = 0; t < run; t++) mxGetPr(scores)[t] = mxGetPr(sc)[t];
+        mxDestroyArray(sc);
+        const char* fields[] = {"R_est", "R_init", "scores"};
+        plhs[0] = mxCreateStructMatrix(1, 1, 3, fields);
+        mxSetField(plhs[0], 0, "R_est", R);
+        mxSetField(plhs[0], 0, "R_init", R0);
+        mxSetField(plhs[0], 0, "scores", scores);
+        return;
+    }
+    if (strcmp(cmd, "spectral") == 0) {
+        if (nrhs != 3) mexErrMsgIdAndTxt("DESC:b200", "spectral: 2 arguments expected");
+        mwSize m;
+        check_inputs(prhs[1], prhs[2], &m);
+        desc_b200_handle* h = NULL;
+        fail_if(desc_b200_create(&h, 0, (int64_t)m, mxGetPr(prhs[1]), mxGetPr(prhs[2]), NULL), NULL);
+        int64_t info[10];
+        fail_if(desc_b200_get_info(h, info), h);
+        mwSize dims[3] = {3, 3, 0};
+        dims[2] = (mwSize)info[0];
+        plhs[0] = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
+        fail_if(desc_b200_spectral(h, mxGetPr(plhs[0])), h);
+        desc_b200_destroy(h);
         return;
     }
     if (strcmp(cmd, "align") == 0) {

@@ -555,9 +555,13 @@ def gcw(Ind, RijMat, S_vec, dense_limit=400, power=1.5):
     n, ei, ej = check_ind(Ind)
     R = to_internal(RijMat)
     S_vec = np.asarray(S_vec, dtype=np.float64).ravel()
-    om = 1.0 / ((S_vec ** 1.5 if power == 1.5 else S_vec) + 1e-8)   # GCW.m:20 / CEMP_GCW.m:141
-    d = np.bincount(ei, om, n) + np.bincount(ej, om, n)          # sum(Weights,2), GCW.m:21
-    isd = 1.0 / np.sqrt(d)
+    if power is None:                                            # Spectral.m:36-40: unweighted, un-normalised
+        om = np.ones(ei.size)
+        isd = np.ones(n)
+    else:
+        om = 1.0 / ((S_vec ** 1.5 if power == 1.5 else S_vec) + 1e-8)   # GCW.m:20 / CEMP_GCW.m:141
+        d = np.bincount(ei, om, n) + np.bincount(ej, om, n)      # sum(Weights,2), GCW.m:21
+        isd = 1.0 / np.sqrt(d)
     c = (om * isd[ei] * isd[ej])[:, None, None]
     blk = c * R
     if n <= dense_limit:
@@ -784,6 +788,11 @@ def DESC(Ind, RijMat, params, **kw):
 # --------------------------------------------------------------------------------------------
 # CEMP / CEMP+GCW on the same incidence (Algorithms/CEMP.m, CEMP_GCW.m)
 # --------------------------------------------------------------------------------------------
+def spectral(Ind, RijMat):
+    """``R_est = Spectral(Ind, RijMat)`` (Algorithms/Spectral.m:15-47): GCW.m's pipeline on the plain block matrix."""
+    return gcw(Ind, RijMat, np.ones(np.asarray(Ind).shape[0]), power=None)
+
+
 def cemp_incidence(Ind, nsample=50, seed=0, cycles=None):
     """Cycle lists for CEMP as an ``Incidence`` (IKJ/JKI unused, left empty).
 

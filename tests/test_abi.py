@@ -54,7 +54,7 @@ def test_mex_gateway_compiles_against_stub_header():
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     for shim in ("DESC.m", "DESC_PGD.m", "DESC_init.m", "GCW.m", "CEMP.m", "CEMP_GCW.m", "Rotation_Alignment.m",
-                 "Uniform_Topology.m", "Nonuniform_Topology.m",
+                 "Uniform_Topology.m", "Nonuniform_Topology.m", "MPLS.m", "Spectral.m",
                  "desc_b200_rule.m", "desc_b200_run.m"):
         assert os.path.exists(os.path.join(ROOT, "matlab", shim))
 

@@ -124,3 +124,17 @@ def test_mst_init_edge_cases():
         assert e.value.code == desc_b200._lib.ERR_ARG
         with pytest.raises(desc_b200.DescError):
             s.mst_init()          # no cemp on this handle
+
+
+@pytest.mark.parametrize("case", [(100, 0.5, 0.1, 0.1, 1), (250, 0.2, 0.3, 0.05, 2)])
+def test_spectral_matches_oracle(case):
+    """`R_est = Spectral(Ind, RijMat)` (Algorithms/Spectral.m): GCW's solver on the plain block matrix"""
+    n, p, q, sigma, seed = case
+    mo = O.uniform_topology(n, p, q, sigma, "uniform", rng=400 + seed)
+    R = desc_b200.Spectral(mo["Ind"], mo["RijMat"])
+    assert O.aligned_angle_deg(R, O.spectral(mo["Ind"], mo["RijMat"])).mean() <= ROT_TOL_DEG
+    # a GCW call on the same handle afterwards is unaffected by the weight rule
+    with desc_b200.Solver(mo["Ind"], mo["RijMat"]) as s:
+        s.spectral()
+        Rg = s.gcw(mo["ErrVec"])
+    assert O.aligned_angle_deg(Rg, O.gcw(mo["Ind"], mo["RijMat"], mo["ErrVec"])).mean() <= ROT_TOL_DEG

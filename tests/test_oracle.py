@@ -339,3 +339,21 @@ def test_mst_init_and_mpls_known_answers():
     Ind = np.array([[1.0, 2.0], [3.0, 4.0]])
     with pytest.raises(ValueError):
         O.mst_init(Ind, O.to_matlab(O._rand_rot(2, np.random.default_rng(0))), np.ones(2))
+
+
+def test_spectral_oracle_against_dense_eigendecomposition():
+    """Spectral.m:24-47 literally (dense block matrix, eig) vs the oracle's sparse route"""
+    mo = O.uniform_topology(50, 0.5, 0.1, 0.1, rng=14)
+    n = 50
+    Ind = mo["Ind"].astype(int)
+    B = np.zeros((3 * n, 3 * n))
+    for k in range(Ind.shape[0]):
+        i, j = Ind[k] - 1
+        B[3 * i:3 * i + 3, 3 * j:3 * j + 3] = mo["RijMat"][:, :, k]
+    B = B + B.T
+    lam, V = np.linalg.eigh(B)
+    V = V[:, ::-1][:, :3]
+    if np.linalg.det(V[:3, :]) < 0:
+        V[:, 0] = -V[:, 0]
+    R_lit = O.to_matlab(O.proj_so3(V.reshape(n, 3, 3)))
+    assert O.aligned_angle_deg(O.spectral(mo["Ind"], mo["RijMat"]), R_lit).mean() < 1e-9
