@@ -281,6 +281,14 @@ def run_gpu(args, wl):
         finally:
             s.close()
 
+    # SURVEY 8(f) stages on the same graph, reported beside the metric (not in it); never fatal for the bench line
+    side = None
+    if world == 1 and not args.no_side:
+        try:
+            side = side_stages(desc_b200, Ind_d, R_d, wl, kw, measured_peak()[0], args.seed)
+        except Exception as e:   # noqa: BLE001
+            side = {"error": "%s: %s" % (type(e).__name__, e)}
+
     step_e2e()
     ms_e2e_total, _ = timed(step_e2e, max(1, min(args.steps, 3)))
     ms_e2e = ms_e2e_total / max(1, min(args.steps, 3))
@@ -330,10 +338,51 @@ def run_gpu(args, wl):
                 "stages_ms": {k: tm[k] for k in ("graph_ms", "build_ms", "cycle_ms", "pgd_ms", "gcw_ms", "pgd_iter_ms",
                                                  "pgd_pass1_ms", "pgd_pass2_ms", "pgd_comm_ms")},
                 "gcw_iters": tm["gcw_iters"], "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "cpu_baseline": cpu, "clocks": clocks, "per_rank": per_rank, "laa_refine": laa}
+                "cpu_baseline": cpu, "clocks": clocks, "per_rank": per_rank, "laa_refine": laa,
+                "side_stages": side}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def side_stages(desc_b200, Ind_d, R_d, wl, kw, peak, seed):
+    """CEMP / CEMP+GCW / CEMP+MST / MPLS / Spectral (the comparators Demo/compare_algorithms.m runs beside DESC) with
+    the demo's parameters on the bench graph, and the device generator of that graph; device-timed by the library."""
+    import numpy as np
+    out = {}
+    s = desc_b200.Solver(Ind_d, R_d, n=wl["n"], **kw)
+    try:
+        info = s.build_incidence(n_sample=50, seed=1)                      # CEMP_parameters.nsample = 50
+        s.cycle_inconsistency()
+        beta = 2.0 ** np.arange(6)
+        s.cemp(6, beta)
+        s.cemp(6, beta)                                                     # second call: buffers exist
+        t = s.timings()
+        per = t["cemp_ms"] / 7.0                                            # initial mean + 6 reweightings
+        alg = 16.0 * info["m_cycle"] + 24.0 * info["m"]                     # pk_jk+pk_ki+S0 per slot; rowptr, x in, x out per edge
+        out["cemp"] = {"ms": t["cemp_ms"], "m_cycle": info["m_cycle"], "reweightings": 7, "ms_per_reweighting": per,
+                       "algorithmic_bytes_per_reweighting": alg, "achieved_gbs": alg / (per * 1e-3) / 1e9,
+                       "frac_of_hbm_peak": alg / (per * 1e-3) / 1e9 / peak}
+        s.cemp_gcw()
+        out["cemp_gcw_ms"] = s.timings()["gcw_ms"]
+        s.mst_init()
+        out["cemp_mst_ms"] = s.timings()["mst_ms"]
+        MP = dict(stop_threshold=1e-3, max_iter=100, reweighting=[32.0], thresholding=[0.95, 0.9, 0.85, 0.8],
+                  cycle_info_ratio=1.0 / (np.arange(1, 101) + 1))
+        _, sc = s.mpls_refine(MP)
+        t = s.timings()
+        out["mpls_refine"] = {"ms": t["laa_ms"], "iterations": t["laa_iters"], "cg_iterations": t["laa_cg_iters"],
+                              "final_score": float(sc[-1]) if len(sc) else None}
+        s.spectral()
+        out["spectral_ms"] = s.timings()["gcw_ms"]
+    finally:
+        s.close()
+    for _ in range(2):
+        with desc_b200.Uniform_Topology(wl["n"], wl["p"], wl["q"], wl["sigma"], wl["model"], seed=seed,
+                                        device=kw["device"], on_device=True) as mo:
+            out["generator"] = {"ms": mo.gen_ms, "m": mo.m, "launches": mo.launches,
+                                "output_gbs": (168.0 * mo.m) / (mo.gen_ms * 1e-3) / 1e9}
+    return out
 
 
 def main():
@@ -347,6 +396,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=1500, help="nodes of the CPU-baseline sample graph")
     ap.add_argument("--cpu-iters", type=int, default=100, help="PGD iterations of the CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the SURVEY 8(f) side stages (CEMP, MPLS, ...)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -5,7 +5,8 @@
 
 Every rank solves the same graph (a) alone (world=1) and (b) as its shard of the N-rank solve, and
 checks: identical iters_run, S_vec within 1e-12, objective history within 1e-11,
-rotations within 1e-6 deg.  Prints MULTI_GPU_OK on rank 0 when all ranks agree.
+rotations within 1e-6 deg; CEMP's SVec bit-identical (per-edge arithmetic does not depend on the shard) and
+CEMP+GCW rotations within 1e-6 deg.  Prints MULTI_GPU_OK on rank 0 when all ranks agree.
 """
 import os
 import sys
@@ -27,7 +28,10 @@ def solve(Ind, R, rank, world, nccl_id, local, iters, lr, n_sample):
         s.cycle_inconsistency()
         S, hist, k = s.pgd(iters, desc_b200.ConstantStepSize(lr))
         Rot = s.gcw()
-        return dict(info=info, S=S, hist=hist, k=k, R=Rot, S0=s.S0(), w=s.w())
+        # SURVEY 8(f) #3 on the same sharded incidence: CEMP (edge-sharded reweighting + all-gather) and CEMP+GCW
+        cemp = s.cemp(4, [1.0, 4.0, 16.0])
+        Rc = s.cemp_gcw()
+        return dict(info=info, S=S, hist=hist, k=k, R=Rot, S0=s.S0(), w=s.w(), cemp=cemp, Rc=Rc)
 
 
 def main():
@@ -47,16 +51,18 @@ def main():
         # local slots of the sharded run are a contiguous piece of the single-rank arrays
         a = many["info"]
         rowptr, _ = (None, None)
+        dC = float(np.max(np.abs(one["cemp"] - many["cemp"])))
+        angC = float(O.aligned_angle_deg(one["Rc"], many["Rc"]).mean())
         good = (one["k"] == many["k"] and dS <= 1e-12 and dh <= 1e-11 and ang <= 1e-6 and
-                a["m_cycle"] == one["info"]["m_cycle"])
+                a["m_cycle"] == one["info"]["m_cycle"] and dC == 0.0 and angC <= 1e-6)
         # S0 / w of the shard against the matching slice of the single-rank result
         with desc_b200.Solver(mo["Ind"], mo["RijMat"], device=local) as s1:
             s1.build_incidence(n_sample=ns, seed=5)
             rp, _ = s1.incidence()
         sl = slice(int(rp[a["edge_begin"]]), int(rp[a["edge_end"]]))
         good = good and np.array_equal(one["S0"][sl], many["S0"]) and float(np.max(np.abs(one["w"][sl] - many["w"]), initial=0.0)) <= 1e-12
-        print("rank %d case %d: iters %d/%d dS=%.2e dobj=%.2e dR=%.2e deg shard=[%d,%d) slots=%d %s" % (
-            rank, case, one["k"], many["k"], dS, dh, ang, a["edge_begin"], a["edge_end"], a["local_slots"],
+        print("rank %d case %d: iters %d/%d dS=%.2e dobj=%.2e dR=%.2e deg dCEMP=%.1e dR_cemp=%.2e shard=[%d,%d) slots=%d %s" % (
+            rank, case, one["k"], many["k"], dS, dh, ang, dC, angC, a["edge_begin"], a["edge_end"], a["local_slots"],
             "ok" if good else "MISMATCH"), flush=True)
         ok = ok and good
     t = torch.tensor([1 if ok else 0], device="cuda")
