@@ -102,3 +102,43 @@ def pgd_sharded(inc, S0, iters, lr, rank, world, bounds, allreduce, allgather, p
         else:
             misses = 0
     return S, np.array(hist).reshape(-1, 2), iters_run
+
+
+def cemp_sharded(inc, S0, max_iter, reweighting, rank, world, bounds, allgather):
+    """CEMP.m:98-129 the way libdesc_b200 runs it on N GPUs (csrc/cemp.cu): every rank reweights its own contiguous
+    edge range from the full vector of the previous iteration, then the ranges are all-gathered.  Per-edge
+    arithmetic does not depend on the shard, so the result is bit-identical to ``desc_oracle.cemp``."""
+    from .desc_oracle import cemp_betas
+    m = inc.m
+    st = shard_state_light(inc, S0, rank, bounds)
+    x = np.ones(m)
+
+    def reweight(x_cur, beta, first):
+        out = x_cur.copy()
+        loc = np.ones(st["e1"] - st["e0"])
+        if st["counts"].size:
+            W = np.ones(st["S0"].size) if first else np.exp(-beta * (x_cur[st["e_ki"]] + x_cur[st["e_jk"]]))
+            wsum = np.add.reduceat(W, st["starts"])
+            loc[st["has"]] = np.add.reduceat(W / np.repeat(wsum, st["counts"]) * st["S0"], st["starts"]) if not first \
+                else np.add.reduceat(st["S0"], st["starts"]) / st["counts"]
+        out[st["e0"]:st["e1"]] = loc
+        return allgather(out, bounds)
+
+    x = reweight(x, 0.0, True)
+    for beta in cemp_betas(max_iter, reweighting):
+        x = reweight(x, beta, False)
+    return x
+
+
+def shard_state_light(inc, S0, rank, bounds):
+    """slot range of ``rank`` for incidences without reciprocal maps (CEMP)"""
+    ns_all = np.zeros(inc.m, dtype=np.int64)
+    ns_all[inc.pos_edges] = np.diff(inc.rowptr)
+    rowptr_all = np.concatenate([[0], np.cumsum(ns_all)])
+    e0, e1 = int(bounds[rank]), int(bounds[rank + 1])
+    sl = slice(int(rowptr_all[e0]), int(rowptr_all[e1]))
+    local = np.arange(e0, e1)
+    has = ns_all[local] > 0
+    counts = ns_all[local][has]
+    starts = (rowptr_all[local][has] - rowptr_all[e0]).astype(np.int64)
+    return dict(e0=e0, e1=e1, e_jk=inc.e_jk[sl], e_ki=inc.e_ki[sl], S0=S0[sl], has=has, counts=counts, starts=starts)

@@ -1,6 +1,6 @@
 """World-size-2 tests of the multi-GPU path on CPU (gloo): rendezvous helpers, slot-balanced
-sharding, and the sharded scatter-form PGD (the algorithm libdesc_b200 runs over NCCL) against the
-single-process oracle."""
+sharding, the sharded scatter-form PGD and the sharded CEMP reweighting (the algorithms libdesc_b200 runs over
+NCCL) against the single-process oracle."""
 import os
 import socket
 import sys
@@ -27,7 +27,7 @@ def _worker(rank, world, port, q):
     try:
         from desc_b200 import dist as ddist
         from oracle import desc_oracle as O
-        from oracle.desc_sharded import pgd_sharded
+        from oracle.desc_sharded import pgd_sharded, cemp_sharded
 
         ident = ddist.exchange_nccl_id(lambda: bytes(range(128)))
         assert ident == bytes(range(128))
@@ -57,6 +57,9 @@ def _worker(rank, world, port, q):
         S_ref, hist_ref, k_ref = O.pgd(inc, S0, 40, O.ConstantStepSize(0.02))
         ok = (k == k_ref and np.max(np.abs(S - S_ref)) <= 1e-12 and
               np.max(np.abs(hist[:, 1] - hist_ref[:, 1]) / np.abs(hist_ref[:, 1])) <= 1e-11)
+        # CEMP on the same shards (csrc/cemp.cu: local reweighting + all-gather): bit-identical to the single-rank oracle
+        beta = [1.0, 4.0, 16.0]
+        ok = ok and np.array_equal(cemp_sharded(inc, S0, 5, beta, rank, world, bounds, allgather), O.cemp(inc, S0, 5, beta))
         slots = rowptr_all[bounds[rank + 1]] - rowptr_all[bounds[rank]]
         q.put((rank, bool(ok), int(slots), int(inc.m_cycle)))
     finally:
