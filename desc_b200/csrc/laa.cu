@@ -428,10 +428,10 @@ static int laa_quantile(desc_b200_handle* h, const double* X, int64_t m, double 
 
 int desc_laa_impl(desc_b200_handle* h, const double* d_S, const double* d_Rinit, double* d_Rout, int max_iters,
                   double stop_threshold, int* iters_run, double* scores_host, const desc_laa_sched* mpls) {
-    if (h->world > 1) {
-        desc_set_error("desc_b200_refine: the LAA refinement runs on one GPU (call it on a world==1 handle)");
-        return DESC_B200_ERR_STATE;
-    }
+    // Multi-GPU handles: every rank runs the whole refinement on the replicated graph and the all-gathered S_vec
+    // (a 2 ms stage at cfg 4: sharding its CG would cost more in collectives than it saves).  All ranks execute the
+    // same kernels on the same data, so scores / trip counts agree and the collectives inside the MPLS variant's
+    // cycle reweighting (edge-sharded, desc_cemp_reweight) stay in lockstep.
     const int n = h->n;
     const int64_t m = h->m;
     cudaStream_t st = h->stream;

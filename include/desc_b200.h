@@ -180,7 +180,8 @@ int desc_b200_get_gcw_info(desc_b200_handle* h, double info[8]);
    re-weighted Lie-algebraic averaging started from R_init.  S_vec = NULL: the S_vec of the last pgd
    on this handle; R_init = NULL: the rotations of the last gcw (DESC.m:267).  R_out: 3x3xn.  scores
    (may be NULL): the `score` the reference prints per iteration (DESC.m:305), at most 99 values.
-   Stops like the reference: score <= 1e-3 or 99 iterations (DESC.m:272,287).  One GPU only. */
+   Stops like the reference: score <= 1e-3 or 99 iterations (DESC.m:272,287).  On a multi-GPU handle every
+   rank runs the (small) stage on the replicated graph and returns the same result. */
 int desc_b200_refine(desc_b200_handle* h, const double* S_vec, const double* R_init, double* R_out,
                      int32_t* iters_run, double* scores);
 
@@ -205,7 +206,8 @@ int desc_b200_cycle_reweight(desc_b200_handle* h, const double* x, double beta, 
 /* MPLS (Algorithms/MPLS.m:28) = cemp + mst_init + mpls_refine.
    mst_init (MPLS.m:152-195): minimum spanning tree of the graph weighted by SVec+1 (ties broken by the edge index),
    R_1 = I, rotations multiplied along the tree -- the CEMP+MST estimate the demo reports (compare_algorithms.m:77).
-   SVec = NULL: the last cemp.  DESC_B200_ERR_ARG if the graph is not connected.  One GPU.                    */
+   SVec = NULL: the last cemp.  DESC_B200_ERR_ARG if the graph is not connected.  Replicated on every rank of a
+   multi-GPU handle.                                                                                        */
 int desc_b200_mst_init(desc_b200_handle* h, const double* SVec, double* R_out);
 typedef struct desc_b200_mpls_params {
     double stop_threshold;            /* MPLS_parameters.stop_threshold                               */
@@ -220,7 +222,8 @@ typedef struct desc_b200_mpls_params {
 /* mpls_refine (MPLS.m:198-256): Weighted_LAA step, residuals r_ij, h_ij = cycle reweighting of the residuals
    (needs build_incidence + cycle_inconsistency), weights (alpha h + (1-alpha) r)^-0.75 capped at 1e4, edges above the
    tau-quantile set to 1e-4; stops at score <= stop_threshold or max_iter-1 iterations.  SVec = NULL: the last
-   cemp (initial weights); R_init = NULL: the last mst_init.  scores (may be NULL): max_iter doubles.  One GPU. */
+   cemp (initial weights); R_init = NULL: the last mst_init.  scores (may be NULL): max_iter doubles.  On a multi-GPU
+   handle the LAA step is replicated, the cycle reweighting is edge-sharded (all ranks must call it together).    */
 int desc_b200_mpls_refine(desc_b200_handle* h, const double* SVec, const double* R_init,
                           const desc_b200_mpls_params* params, double* R_out, int32_t* iters_run, double* scores);
 

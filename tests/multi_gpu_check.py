@@ -31,7 +31,14 @@ def solve(Ind, R, rank, world, nccl_id, local, iters, lr, n_sample):
         # SURVEY 8(f) #3 on the same sharded incidence: CEMP (edge-sharded reweighting + all-gather) and CEMP+GCW
         cemp = s.cemp(4, [1.0, 4.0, 16.0])
         Rc = s.cemp_gcw()
-        return dict(info=info, S=S, hist=hist, k=k, R=Rot, S0=s.S0(), w=s.w(), cemp=cemp, Rc=Rc)
+        # stages that run replicated on every rank: LAA refinement (DESC.m:265-312), CEMP+MST, MPLS loop
+        Rl, sc_l = s.refine(S_vec=S, R_init=Rot)
+        Rm0 = s.mst_init()
+        MP = dict(stop_threshold=1e-3, max_iter=20, reweighting=[16.0], thresholding=[0.95, 0.9, 0.85, 0.8],
+                  cycle_info_ratio=1.0 / (np.arange(1, 21) + 1))
+        Rm, sc_m = s.mpls_refine(MP)
+        return dict(info=info, S=S, hist=hist, k=k, R=Rot, S0=s.S0(), w=s.w(), cemp=cemp, Rc=Rc, Rl=Rl, sc_l=sc_l,
+                    Rm0=Rm0, Rm=Rm, sc_m=sc_m)
 
 
 def main():
@@ -55,14 +62,19 @@ def main():
         angC = float(O.aligned_angle_deg(one["Rc"], many["Rc"]).mean())
         good = (one["k"] == many["k"] and dS <= 1e-12 and dh <= 1e-11 and ang <= 1e-6 and
                 a["m_cycle"] == one["info"]["m_cycle"] and dC == 0.0 and angC <= 1e-6)
+        angL = float(O.aligned_angle_deg(one["Rl"], many["Rl"]).mean())
+        angM = float(O.aligned_angle_deg(one["Rm"], many["Rm"]).mean())
+        good = (good and one["sc_l"].size == many["sc_l"].size and one["sc_m"].size == many["sc_m"].size and
+                angL <= 1e-6 and angM <= 1e-6 and np.array_equal(one["Rm0"], many["Rm0"]) and
+                float(np.max(np.abs(one["sc_m"] - many["sc_m"]), initial=0.0)) <= 1e-9)
         # S0 / w of the shard against the matching slice of the single-rank result
         with desc_b200.Solver(mo["Ind"], mo["RijMat"], device=local) as s1:
             s1.build_incidence(n_sample=ns, seed=5)
             rp, _ = s1.incidence()
         sl = slice(int(rp[a["edge_begin"]]), int(rp[a["edge_end"]]))
         good = good and np.array_equal(one["S0"][sl], many["S0"]) and float(np.max(np.abs(one["w"][sl] - many["w"]), initial=0.0)) <= 1e-12
-        print("rank %d case %d: iters %d/%d dS=%.2e dobj=%.2e dR=%.2e deg dCEMP=%.1e dR_cemp=%.2e shard=[%d,%d) slots=%d %s" % (
-            rank, case, one["k"], many["k"], dS, dh, ang, dC, angC, a["edge_begin"], a["edge_end"], a["local_slots"],
+        print("rank %d case %d: iters %d/%d dS=%.2e dobj=%.2e dR=%.2e deg dCEMP=%.1e dR_cemp=%.2e dR_laa=%.1e dR_mpls=%.1e shard=[%d,%d) slots=%d %s" % (
+            rank, case, one["k"], many["k"], dS, dh, ang, dC, angC, angL, angM, a["edge_begin"], a["edge_end"], a["local_slots"],
             "ok" if good else "MISMATCH"), flush=True)
         ok = ok and good
     t = torch.tensor([1 if ok else 0], device="cuda")

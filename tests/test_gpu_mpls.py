@@ -138,3 +138,21 @@ def test_spectral_matches_oracle(case):
         s.spectral()
         Rg = s.gcw(mo["ErrVec"])
     assert O.aligned_angle_deg(Rg, O.gcw(mo["Ind"], mo["RijMat"], mo["ErrVec"])).mean() <= ROT_TOL_DEG
+
+
+def test_demo_compare_algorithms_table():
+    """demo/compare_algorithms.py = Demo/compare_algorithms.m on the device: every row is produced, the robust
+    methods beat the plain spectral one on a corrupted graph and the refinement does not hurt"""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("compare_algorithms", os.path.join(root, "demo", "compare_algorithms.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rows, extra = mod.run(n=100, p=0.5, q=0.2, sigma=0.1, seed=0)
+    err = {name: mean for name, mean, _ in rows}
+    assert list(err) == ["Spectral", "CEMP+MST", "CEMP+GCW", "MPLS", "DESC_init", "DESC"]
+    assert all(np.isfinite(v) and 0.0 <= v < 30.0 for v in err.values())
+    assert err["MPLS"] < err["CEMP+MST"] and err["DESC"] < err["Spectral"] and err["CEMP+GCW"] < err["Spectral"]
+    assert err["DESC"] <= err["DESC_init"] + 0.5
+    assert float(np.mean(np.abs(extra["S_vec"].ravel() - extra["ErrVec"].ravel()))) < 0.05
