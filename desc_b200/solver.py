@@ -486,9 +486,20 @@ def DESC_PGD(Ind, RijMat, params, **solver_kw):
     return S_vec
 
 
+def _dlmwrite_append(path, row):
+    """``dlmwrite(path, row, 'delimiter', ',', '-append')``: one comma-separated line, 5 significant digits."""
+    with open(path, "a") as f:
+        f.write(",".join("%.5g" % float(v) for v in row) + "\n")
+
+
 def DESC_init(Ind, RijMat, params, **solver_kw):
-    """``[R_est, S_vec] = DESC_init(Ind, RijMat, params)`` (Algorithms/DESC_init.m:14)."""
+    """``[R_est, S_vec] = DESC_init(Ind, RijMat, params)`` (Algorithms/DESC_init.m:14).  With ``make_plots`` the
+    reference also appends the convergence curves to two CSV files in the working directory
+    (DESC_init.m:261-262); so does this."""
     S_vec, R, _ = _run_pgd(Ind, RijMat, params, True, **solver_kw)
+    if _param(params, "make_plots", False) and last_diagnostics is not None:
+        _dlmwrite_append("linear_convergence_rotation_error.csv", last_diagnostics["MSE_means"])
+        _dlmwrite_append("linear_convergence_svec_error.csv", last_diagnostics["svec_errors"])
     return R, S_vec
 
 

@@ -134,7 +134,7 @@ def test_rotation_alignment_matches_oracle(n):
     assert mean_err < 1e-5 and med_err < 1e-5
 
 
-def test_make_plots_diagnostics_match_oracle():
+def test_make_plots_diagnostics_match_oracle(monkeypatch, tmp_path):
     """DESC.m:235-239: svec_errors, MSE_means, MSE_medians per iteration; the iterates are untouched"""
     mo = O.uniform_topology(150, 0.5, 0.25, 0.1, "uniform", rng=51)
     iters, lr, ns, seed = 12, 0.05, 20, 3
@@ -159,8 +159,13 @@ def test_make_plots_diagnostics_match_oracle():
     import desc_b200.solver as SV
     params = dict(iters=iters, Gradient=desc_b200.ConstantStepSize(lr), make_plots=True, ErrVec=mo["ErrVec"],
                   R_orig=mo["R_orig"], n_sample=ns, seed=seed)
+    monkeypatch.chdir(tmp_path)       # DESC_init.m:261-262 appends the curves to CSV files in the working directory
     R, S2 = desc_b200.DESC_init(mo["Ind"], mo["RijMat"], params)
     np.testing.assert_array_equal(S2.ravel(), S)
+    rot = np.loadtxt(tmp_path / "linear_convergence_rotation_error.csv", delimiter=",", ndmin=1)
+    sv = np.loadtxt(tmp_path / "linear_convergence_svec_error.csv", delimiter=",", ndmin=1)
+    assert rot.shape == (run,) and sv.shape == (run,)
+    np.testing.assert_allclose(sv, diag[:, 0], rtol=1e-4)
     d = SV.last_diagnostics
     np.testing.assert_array_equal(d["svec_errors"], diag[:, 0])
     np.testing.assert_array_equal(d["obj_vals"], hist[:, 1])
