@@ -357,3 +357,37 @@ def test_spectral_oracle_against_dense_eigendecomposition():
         V[:, 0] = -V[:, 0]
     R_lit = O.to_matlab(O.proj_so3(V.reshape(n, 3, 3)))
     assert O.aligned_angle_deg(O.spectral(mo["Ind"], mo["RijMat"]), R_lit).mean() < 1e-9
+
+
+def test_weighted_laa_matches_the_literal_least_squares():
+    """Weighted_LAA.m:38 solves ``(diag(Weights)*Amatrix) \\ (Weights.*B)`` (sparse QR in MATLAB); the oracle goes
+    through the normal equations.  Cross-check one step against a dense QR least-squares of the literal formula,
+    with weights spanning the reference's clamp range 1e-4 .. 1e4 (condition number of the squared system ~1e16)."""
+    rng = np.random.default_rng(21)
+    mo = O.uniform_topology(30, 0.6, 0.2, 0.1, "uniform", rng=21)
+    n, ei, ej = O.check_ind(mo["Ind"])
+    A = O.build_amatrix(ei, ej, n)
+    RR = np.transpose(mo["RijMat"], (1, 0, 2))
+    Q = O.R2Q(O.to_matlab(O._rand_rot(n, rng)))
+    QQ = O.R2Q(RR)
+    for Weights in (np.ones(ei.size), 10.0 ** rng.uniform(-2, 2, ei.size)):
+        Qn, W, B, score = O.weighted_laa(ei, ej, Q, QQ, A, Weights)
+        X_lit, *_ = np.linalg.lstsq(Weights[:, None] * A.toarray(), Weights[:, None] * B, rcond=None)
+        np.testing.assert_allclose(np.linalg.norm(X_lit, axis=1).sum() / n, score, rtol=1e-9)
+        theta = np.linalg.norm(X_lit, axis=1)
+        Wv = X_lit * (np.sin(theta / 2.0) / theta)[:, None]
+        np.testing.assert_allclose(W[1:, 1:4], Wv, rtol=1e-7, atol=1e-12)
+        np.testing.assert_allclose(np.linalg.norm(Qn, axis=1), np.linalg.norm(Q, axis=1), rtol=1e-12)   # unit update
+
+
+def test_cemp_csr_vs_literal_on_random_draws():
+    """more with-replacement draws than the two fixtures: CSR CEMP == literal dense CEMP (CEMP.m:25-131)"""
+    from oracle.desc_literal import cemp_literal, cemp_draw
+    for seed, (n, p, ns, T) in enumerate([(25, 0.5, 6, 3), (30, 0.25, 4, 5), (20, 0.9, 15, 2)]):
+        mo = O.uniform_topology(n, p, 0.3, 0.1, "uniform", rng=50 + seed)
+        P = dict(max_iter=T, reweighting=[0.5, 2.0, 7.0][:max(1, T - 1)], nsample=ns)
+        Co, ptr, apex = cemp_draw(mo["Ind"], ns, 70 + seed)
+        S_lit, ex = cemp_literal(mo["Ind"], mo["RijMat"], P, Co)
+        inc = O.cemp_incidence(mo["Ind"], cycles=(ptr, apex))
+        S = O.cemp(inc, O.cycle_inconsistency(inc, mo["RijMat"]), T, P["reweighting"])
+        np.testing.assert_allclose(S, S_lit, rtol=1e-12, atol=1e-15)
