@@ -391,3 +391,27 @@ def test_cemp_csr_vs_literal_on_random_draws():
         inc = O.cemp_incidence(mo["Ind"], cycles=(ptr, apex))
         S = O.cemp(inc, O.cycle_inconsistency(inc, mo["RijMat"]), T, P["reweighting"])
         np.testing.assert_allclose(S, S_lit, rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("case", [(36, 0.55, 0.25, 0.05, 7, 1), (30, 0.7, 0.1, 0.0, 5, 2), (40, 0.35, 0.3, 0.1, 9, 3)])
+def test_csr_oracle_vs_literal_on_random_graphs_and_sample_order(case):
+    """beyond the fixed fixtures: random graphs, and MATLAB's datasample order.  `datasample` returns the kept
+    apices in random order (DESC.m:84); the CSR oracle and the device store them ascending.  The literal
+    restatement run with a random order per edge must give the same S_vec (order only changes the FP summation
+    order inside an edge), and the CSR oracle must match the literal one."""
+    from oracle.desc_literal import desc_literal
+    n, p, q, sigma, ns, seed = case
+    mo = O.uniform_topology(n, p, q, sigma, "uniform", rng=300 + seed)
+    params = dict(iters=25, Gradient=O.ConstantStepSize(0.02))
+    _, S_sorted, ex = desc_literal(mo["Ind"], mo["RijMat"], params, seed=seed, n_sample=ns, run_gcw=False)
+    _, S_perm, ex_p = desc_literal(mo["Ind"], mo["RijMat"], dict(params, Gradient=O.ConstantStepSize(0.02)), seed=seed,
+                                   n_sample=ns, permute_rng=np.random.default_rng(seed), run_gcw=False)
+    assert ex["iters_run"] == ex_p["iters_run"]
+    np.testing.assert_allclose(S_perm, S_sorted, rtol=1e-11, atol=1e-14)
+    np.testing.assert_allclose(ex_p["hist"][:, 1], ex["hist"][:, 1], rtol=1e-11)
+    inc = O.build_incidence(mo["Ind"], n_sample=ns, seed=seed)
+    S0 = O.cycle_inconsistency(inc, mo["RijMat"])
+    np.testing.assert_array_equal(S0, ex["S0_long"])
+    S_csr, hist, k = O.pgd(inc, S0, 25, O.ConstantStepSize(0.02))
+    assert k == ex["iters_run"]
+    np.testing.assert_allclose(S_csr, S_sorted, rtol=1e-11, atol=1e-14)
