@@ -157,3 +157,48 @@ def nonuniform_topology(n, p, p_node_crpt, p_edge_crpt, sigma_in, sigma_out, crp
     Ind = np.stack([ei + 1, ej + 1], axis=1).astype(np.float64)
     return dict(Ind=Ind, RijMat=to_matlab(RijMat), Rij_orig=to_matlab(Rij_orig), R_orig=to_matlab(R_orig),
                 ErrVec=ErrVec, corrupted=crpt)
+
+
+def nonuniform_topology_sequential(n, p, p_node_crpt, p_edge_crpt, sigma_in, sigma_out, crpt_type="uniform", seed=0):
+    """The same model with the reference's SEQUENTIAL loops kept literally (Nonuniform_Topology.m:80-124: for every
+    corrupted node in ``randperm`` order, for every picked neighbour in ``randperm`` order, overwrite the edge), the
+    ``randperm`` orders being the key orders of the counter-based draws.  Exists to check the per-edge rules of
+    ``nonuniform_topology`` (and of ``csrc/gen.cu``) against the loop they replace."""
+    ei, ej = graph(n, p, seed)
+    m = ei.size
+    e = np.arange(m, dtype=np.int64)
+    R_orig = rand_rot(seed, S_RORIG, np.arange(n))
+    Rij_orig = R_orig[ei] @ R_orig[ej].transpose(0, 2, 1)
+    RijMat = Rij_orig.copy()
+    IndMat = {}
+    for k in range(m):                                                               # :57-58
+        IndMat[(int(ei[k]), int(ej[k]))] = k + 1
+        IndMat[(int(ej[k]), int(ei[k]))] = -(k + 1)
+    nodes = np.arange(n, dtype=np.int64)
+    node_crpt = np.lexsort((nodes, u64(seed, S_NODEPERM, nodes, 0)))                 # randperm(n), :62
+    node_crpt = node_crpt[: int(math.floor(n * p_node_crpt))]                        # :63-64
+    crptInd = np.zeros(m, dtype=bool)
+    R_crpt = rand_rot(seed, S_RCORR, nodes)
+    full_a = np.concatenate([ej, ei])                                                # Ind_full, :42
+    full_b = np.concatenate([ei, ej])
+    for i in node_crpt:                                                              # :80
+        cand = full_b[full_a == i]                                                   # :81
+        perm = np.lexsort((cand, u64(seed, S_NBRPERM, np.full(cand.size, i), cand)))  # randperm(length(cand)), :83
+        nn = int(math.floor(p_edge_crpt * cand.size))                                # :84
+        for j in cand[perm[:nn]]:                                                    # :88
+            k = IndMat[(int(i), int(j))]
+            ke = abs(k) - 1
+            crptInd[ke] = True
+            if crpt_type == "uniform":
+                M = rand_rot(seed, S_R0, np.array([2 * ke + (0 if k > 0 else 1)]))[0]   # a fresh draw per visit, :91-94
+            elif crpt_type == "self-consistent":
+                M = R_crpt[i] @ R_crpt[j].T
+            else:
+                M = R_crpt[i] @ R_orig[j].T
+            RijMat[ke] = M if k > 0 else M.T                                         # :97-101
+    noise = ~crptInd
+    RijMat[noise] = RijMat[noise] + sigma_in * randn3(seed, S_NOISE, e[noise])
+    RijMat[crptInd] = RijMat[crptInd] + sigma_out * randn3(seed, S_NOISE_OUT, e[crptInd])
+    RijMat = proj_so3(RijMat)
+    return dict(Ind=np.stack([ei + 1, ej + 1], axis=1).astype(np.float64), RijMat=to_matlab(RijMat),
+                ErrVec=_err_vec(Rij_orig, RijMat), corrupted=crptInd)

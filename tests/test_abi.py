@@ -171,3 +171,17 @@ def test_counter_generators_follow_the_reference_structure():
     cdeg = np.bincount(np.concatenate([i[mo["corrupted"]], j[mo["corrupted"]]]), minlength=n)
     heavy = cdeg >= np.floor(0.5 * deg)                               # the corrupted nodes
     assert heavy.sum() >= int(np.floor(n * 0.3))
+
+
+@pytest.mark.parametrize("crpt_type", ["uniform", "self-consistent", "adv"])
+def test_nonuniform_per_edge_rules_equal_the_sequential_loops(crpt_type):
+    """csrc/gen.cu (and its numpy twin) replace the reference's sequential corruption loops
+    (Nonuniform_Topology.m:80-124) by per-edge rules; check the rules against the loops kept literally."""
+    from oracle import desc_models_ctr as M
+    for seed, (n, p, pn, pe) in enumerate([(40, 0.5, 0.4, 0.6), (35, 0.3, 1.0, 1.0), (30, 0.6, 0.2, 0.1)]):
+        a = M.nonuniform_topology(n, p, pn, pe, 0.05, 0.1, crpt_type, seed=seed)
+        b = M.nonuniform_topology_sequential(n, p, pn, pe, 0.05, 0.1, crpt_type, seed=seed)
+        np.testing.assert_array_equal(a["Ind"], b["Ind"])
+        np.testing.assert_array_equal(a["corrupted"], b["corrupted"])
+        np.testing.assert_allclose(a["RijMat"], b["RijMat"], atol=1e-13)
+        np.testing.assert_allclose(a["ErrVec"], b["ErrVec"], atol=1e-9)
