@@ -5,9 +5,9 @@ package is the thin host-side mirror of the reference's MATLAB interface.  No CP
 """
 from ._lib import DescError, LIB_PATH  # noqa: F401
 from .solver import (ConstantStepSize, PiecewiseStepSize, HybridGradient, Solver, DESC, DESC_PGD,  # noqa: F401
-                     DESC_init, GCW, CEMP, CEMP_GCW, MPLS, Spectral, Rotation_Alignment, device_count, nccl_unique_id)
+                     DESC_init, GCW, CEMP, CEMP_GCW, MPLS, Spectral, Rotation_Alignment, cycles_from_desc, cycles_from_cemp, device_count, nccl_unique_id)
 
 from .models import Uniform_Topology, Nonuniform_Topology, Ring_Topology, Model  # noqa: F401
 
 __all__ = ["Uniform_Topology", "Nonuniform_Topology", "Ring_Topology", "Model", "ConstantStepSize", "PiecewiseStepSize", "HybridGradient", "Solver", "DESC", "DESC_PGD", "DESC_init",
-           "GCW", "CEMP", "CEMP_GCW", "MPLS", "Spectral", "Rotation_Alignment", "device_count", "nccl_unique_id", "DescError", "LIB_PATH"]
+           "GCW", "CEMP", "CEMP_GCW", "MPLS", "Spectral", "Rotation_Alignment", "cycles_from_desc", "cycles_from_cemp", "device_count", "nccl_unique_id", "DescError", "LIB_PATH"]

@@ -401,6 +401,38 @@ def nccl_unique_id():
 
 
 # ---------------------------------------------------------------------------------------
+# Replaying a MATLAB draw: the reference's cycle lists -> the (ptr, apex) lists ``cycles=`` takes
+# ---------------------------------------------------------------------------------------
+def cycles_from_desc(cum_ind, CoDeg_pos_ind, IJK, m):
+    """DESC.m's ``cum_ind`` (m_pos+1), ``CoDeg_pos_ind`` (1-based ids of the edges with a 3-cycle, :36) and ``IJK``
+    (1-based apex per slot, :93) -> ``(ptr over ALL m edges, 0-based apex)``."""
+    cum_ind = np.asarray(cum_ind, dtype=np.int64).ravel()
+    pos = np.asarray(CoDeg_pos_ind, dtype=np.int64).ravel() - 1
+    cnt = np.zeros(int(m), dtype=np.int64)
+    cnt[pos] = np.diff(cum_ind)
+    ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    apex = (np.asarray(IJK, dtype=np.int64).ravel() - 1).astype(np.int32)
+    if apex.size != int(ptr[-1]):
+        raise ValueError("IJK must have cum_ind(end) entries")
+    return ptr, apex
+
+
+def cycles_from_cemp(CoIndMat):
+    """CEMP.m's / MPLS.m's ``CoIndMat`` (nsample x m, 1-based apices; all-zero columns for edges without a 3-cycle,
+    :63) -> ``(ptr over ALL m edges, 0-based apex)``.  Repeated apices (the draw is WITH replacement) are kept."""
+    Co = np.asarray(CoIndMat, dtype=np.int64)
+    if Co.ndim != 2:
+        raise ValueError("CoIndMat must be nsample x m")
+    has = (Co > 0).all(axis=0)
+    if ((Co > 0).any(axis=0) != has).any():
+        raise ValueError("a CoIndMat column must be all zero (no 3-cycle) or all positive")
+    cnt = np.where(has, Co.shape[0], 0).astype(np.int64)
+    ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    apex = (Co.T[has].ravel() - 1).astype(np.int32)
+    return ptr, apex
+
+
+# ---------------------------------------------------------------------------------------
 # The reference's entry points
 # ---------------------------------------------------------------------------------------
 def _param(params, key, default=None):

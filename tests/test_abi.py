@@ -185,3 +185,22 @@ def test_nonuniform_per_edge_rules_equal_the_sequential_loops(crpt_type):
         np.testing.assert_array_equal(a["corrupted"], b["corrupted"])
         np.testing.assert_allclose(a["RijMat"], b["RijMat"], atol=1e-13)
         np.testing.assert_allclose(a["ErrVec"], b["ErrVec"], atol=1e-9)
+
+
+def test_matlab_cycle_list_converters():
+    """host-side plumbing for replaying a MATLAB draw through ``cycles=`` (no compute, no GPU)"""
+    from conftest import golden_names, cemp_golden_names, load_golden, golden_csr
+    g = load_golden(golden_names()[0])
+    ptr, apex = desc_b200.cycles_from_desc(g["cum_ind"], g["CoDeg_pos_ind"], g["IJK"], g["Ind"].shape[0])
+    ptr2, apex2 = golden_csr(g)
+    np.testing.assert_array_equal(ptr, ptr2)
+    np.testing.assert_array_equal(apex, apex2)
+    for name in cemp_golden_names():
+        g = load_golden(name)
+        ptr, apex = desc_b200.cycles_from_cemp(g["CoIndMat"])
+        np.testing.assert_array_equal(ptr, g["cyc_ptr"])
+        np.testing.assert_array_equal(apex, g["cyc_apex"])
+    with pytest.raises(ValueError):
+        desc_b200.cycles_from_cemp(np.array([[1, 0], [0, 0]]))
+    with pytest.raises(ValueError):
+        desc_b200.cycles_from_desc([0, 2], [1], [3], 2)
