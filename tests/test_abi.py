@@ -204,3 +204,30 @@ def test_matlab_cycle_list_converters():
         desc_b200.cycles_from_cemp(np.array([[1, 0], [0, 0]]))
     with pytest.raises(ValueError):
         desc_b200.cycles_from_desc([0, 2], [1], [3], 2)
+
+
+def test_mat_file_round_trip(tmp_path):
+    """the .mat twins of the fixtures load into the layout the entry points take; results save in MATLAB's shapes"""
+    import scipy.io
+    from conftest import GOLDEN_DIR, golden_names, load_golden
+    name = golden_names()[0]
+    g = load_golden(name)
+    mo = desc_b200.load_mat(os.path.join(GOLDEN_DIR, name + ".mat"))
+    np.testing.assert_array_equal(mo["Ind"], g["Ind"])
+    np.testing.assert_array_equal(mo["RijMat"], g["RijMat"])
+    np.testing.assert_array_equal(mo["R_orig"], g["R_orig"])
+    np.testing.assert_array_equal(mo["ErrVec"], g["ErrVec"].ravel())
+    assert mo["RijMat"].flags.f_contiguous and mo["Ind"].flags.f_contiguous
+    # a struct variable, as `save('graph.mat', 'model_out')` writes it
+    p = tmp_path / "graph.mat"
+    scipy.io.savemat(p, {"model_out": {"Ind": g["Ind"], "RijMat": g["RijMat"], "ErrVec": g["ErrVec"]}})
+    mo2 = desc_b200.load_mat(p)
+    np.testing.assert_array_equal(mo2["Ind"], g["Ind"])
+    np.testing.assert_array_equal(mo2["RijMat"], g["RijMat"])
+    q = tmp_path / "res.mat"
+    desc_b200.save_mat(q, S_vec=g["S_vec"], R_est=g["R_est"])
+    back = scipy.io.loadmat(q)
+    assert back["S_vec"].shape == (1, g["Ind"].shape[0]) and back["R_est"].shape == g["R_est"].shape
+    with pytest.raises(ValueError):
+        scipy.io.savemat(tmp_path / "bad.mat", {"x": np.zeros(3)})
+        desc_b200.load_mat(tmp_path / "bad.mat")
