@@ -22,7 +22,12 @@ def _all_golden():
 
 def golden_names():
     """the DESC fixtures (DESC.m:14-312)"""
-    return [n for n in _all_golden() if not n.startswith("cemp_")]
+    return [n for n in _all_golden() if not n.startswith(("cemp_", "gen_"))]
+
+
+def gen_golden_names():
+    """outputs of the counter-based generators for fixed seeds"""
+    return [n for n in _all_golden() if n.startswith("gen_")]
 
 
 def cemp_golden_names():

@@ -24,6 +24,7 @@ outputs on it (``S0Mat``, ``SVec`` after every reweighting, ``R_est``), the alig
 
     python tests/golden/make_golden.py            # everything
     python tests/golden/make_golden.py cemp       # only the fixtures whose name starts with "cemp"
+    python tests/golden/make_golden.py gen        # only the generator fixtures (counter-based draws)
 """
 import os
 import sys
@@ -94,6 +95,23 @@ def make_cemp(prefix):
             name, a["n"], mo["Ind"].shape[0], apex.size, np.mean(np.abs(SVec - mo["ErrVec"])), mean_err, med_err))
 
 
+def make_generators(prefix):
+    """``gen_*.npz``: outputs of the counter-based generators (oracle/desc_models_ctr.py == csrc/gen.cu) for fixed
+    seeds -- pins the draw specification (streams, mixing constants, Box-Muller pairing) against accidental change."""
+    from oracle import desc_models_ctr as M
+    cases = [("gen_uniform_n24", lambda: M.uniform_topology(24, 0.5, 0.3, 0.1, "uniform", seed=5)),
+             ("gen_selfconsistent_n20", lambda: M.uniform_topology(20, 0.6, 0.4, 0.05, "self-consistent", seed=6)),
+             ("gen_ring_n40_w6", lambda: M.uniform_topology(40, 0.5, 0.2, 0.1, "uniform", seed=7, ring=6)),
+             ("gen_nonuniform_n24_adv", lambda: M.nonuniform_topology(24, 0.5, 0.4, 0.5, 0.05, 0.1, "adv", seed=8))]
+    for name, fn in cases:
+        if not name.startswith(prefix):
+            continue
+        mo = fn()
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), Ind=mo["Ind"], RijMat=mo["RijMat"], R_orig=mo["R_orig"],
+                            ErrVec=mo["ErrVec"], corrupted=mo["corrupted"])
+        print("%-26s m=%d corrupted=%d" % (name, mo["Ind"].shape[0], int(mo["corrupted"].sum())))
+
+
 def make_rule(spec):
     if spec[0] == "const":
         return O.ConstantStepSize(spec[1])
@@ -105,6 +123,7 @@ def make_rule(spec):
 def main():
     prefix = sys.argv[1] if len(sys.argv) > 1 else ""
     make_cemp(prefix)
+    make_generators(prefix)
     for idx, (name, gen, args, ns, seed, rule_spec, iters) in enumerate(CASES):
         if not name.startswith(prefix):
             continue

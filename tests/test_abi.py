@@ -231,3 +231,21 @@ def test_mat_file_round_trip(tmp_path):
     with pytest.raises(ValueError):
         scipy.io.savemat(tmp_path / "bad.mat", {"x": np.zeros(3)})
         desc_b200.load_mat(tmp_path / "bad.mat")
+
+
+def test_counter_generators_reproduce_their_fixtures():
+    """the draw specification shared by csrc/gen.cu and oracle/desc_models_ctr.py is pinned by committed outputs"""
+    from conftest import gen_golden_names, load_golden
+    from oracle import desc_models_ctr as M
+    makers = {"gen_uniform_n24": lambda: M.uniform_topology(24, 0.5, 0.3, 0.1, "uniform", seed=5),
+              "gen_selfconsistent_n20": lambda: M.uniform_topology(20, 0.6, 0.4, 0.05, "self-consistent", seed=6),
+              "gen_ring_n40_w6": lambda: M.uniform_topology(40, 0.5, 0.2, 0.1, "uniform", seed=7, ring=6),
+              "gen_nonuniform_n24_adv": lambda: M.nonuniform_topology(24, 0.5, 0.4, 0.5, 0.05, 0.1, "adv", seed=8)}
+    names = gen_golden_names()
+    assert sorted(names) == sorted(makers)
+    for name in names:
+        g, mo = load_golden(name), makers[name]()
+        np.testing.assert_array_equal(mo["Ind"], g["Ind"])
+        np.testing.assert_array_equal(mo["corrupted"], g["corrupted"])
+        np.testing.assert_allclose(mo["RijMat"], g["RijMat"], atol=1e-12, rtol=0)
+        np.testing.assert_allclose(mo["R_orig"], g["R_orig"], atol=1e-12, rtol=0)
