@@ -25,10 +25,28 @@ static int cmp_double(const void* a, const void* b) {
     return (x > y) - (x < y);
 }
 
+/* ascending sort of the edge's candidate weights (DESC.m:215): insertion sort for the short lists the sampler
+   produces, qsort beyond */
+static void sort_asc(double* a, int n) {
+    if (n > 64) {
+        qsort(a, (size_t)n, sizeof(double), cmp_double);
+        return;
+    }
+    for (int i = 1; i < n; i++) {
+        const double v = a[i];
+        int j = i - 1;
+        while (j >= 0 && a[j] > v) {
+            a[j + 1] = a[j];
+            j--;
+        }
+        a[j + 1] = v;
+    }
+}
+
 /* returns iterations run.  hist: 2*iters doubles [average_change, obj] per iteration.
  * rule_kind 0: step = -lr*grad ; 1: t++, step = -lr/(fix(t/decay)+1)*grad (t_io is read and advanced) */
 int desc_c_pgd(int64_t m, int64_t m_pos, const int64_t* pos_edges, const int64_t* rowptr,
-               const int64_t* e_jk, const int64_t* e_ki, const int64_t* IKJ, const int64_t* JKI,
+               const int32_t* e_jk, const int32_t* e_ki, const int64_t* IKJ, const int64_t* JKI,
                const double* S0, int iters, int rule_kind, double lr, double decay_interval, int64_t* t_io,
                int patience, double tol, int threads, double* S_vec, double* wijk, double* hist) {
     const int64_t m_cycle = rowptr[m_pos];
@@ -91,7 +109,7 @@ int desc_c_pgd(int64_t m, int64_t m_pos, const int64_t* pos_edges, const int64_t
                     wnew[c] = wijk[c] + (-lr_eff * g);                    /* DESC.m:207 */
                     srt[c - a] = wnew[c];
                 }
-                qsort(srt, (size_t)ns, sizeof(double), cmp_double);       /* DESC.m:215 */
+                sort_asc(srt, ns);                                        /* DESC.m:215 */
                 double T = 0.0;
                 for (int Ti = 0; Ti < ns; Ti++) {                         /* DESC.m:216-223 */
                     double acc = 0.0;
