@@ -184,9 +184,18 @@ __global__ void k_sum_partials(double* __restrict__ own, const double* __restric
     }
     own[i] = acc;
 }
+// the same for 64-bit fixed-point partials (pgd_ell.cuh): integer sums, any order gives the same bits
+__global__ void k_sum_partials_u64(unsigned long long* __restrict__ own, const unsigned long long* __restrict__ scratch,
+                                   int64_t count, int64_t stride, int world) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    unsigned long long acc = own[i];
+    for (int r = 0; r < world - 1; r++) acc += scratch[(int64_t)r * stride + i];
+    own[i] = acc;
+}
 
 int desc_reduce_to_owners(desc_b200_handle* h, double* buf, int width, const std::vector<int64_t>& bounds,
-                          int tail) {
+                          int tail, bool body_u64) {
     if (h->world <= 1) return DESC_B200_OK;
     const int me = h->rank, W = h->world;
     const int64_t total = bounds[W];
@@ -224,8 +233,12 @@ int desc_reduce_to_owners(desc_b200_handle* h, double* buf, int width, const std
     }
     NCCL_TRY(g_nccl.GroupEnd());
     if (my_cnt > 0) {
-        k_sum_partials<<<(unsigned)((my_cnt + 255) / 256), 256, 0, h->stream>>>(buf + bounds[me] * width, scratch, my_cnt,
-                                                                              stride, W, me);
+        if (body_u64)
+            k_sum_partials_u64<<<(unsigned)((my_cnt + 255) / 256), 256, 0, h->stream>>>(
+                (unsigned long long*)(buf + bounds[me] * width), (const unsigned long long*)scratch, my_cnt, stride, W);
+        else
+            k_sum_partials<<<(unsigned)((my_cnt + 255) / 256), 256, 0, h->stream>>>(buf + bounds[me] * width, scratch, my_cnt,
+                                                                                  stride, W, me);
         KERNEL_CHECK(h);
     }
     if (tail > 0) {

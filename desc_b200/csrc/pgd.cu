@@ -598,6 +598,7 @@ __global__ void k_pgd_partials(const double* __restrict__ partial, int nblocks, 
 
 #include "pgd_stream.cuh"
 #include "pgd_passb.cuh"
+#include "pgd_ell.cuh"
 
 template <int G, int EPL, int NCW, int NSW>
 static int launch_stream(desc_b200_handle* h, const BlkArgs& a, int rule_kind, int want_ctas, bool dry) {
@@ -794,6 +795,108 @@ static int launch_iter_any(desc_b200_handle* h, const PgdArgs& a, int rule_kind)
     return DESC_B200_ERR_LIMIT;
 }
 
+// ------------------------------------------------------------------------------------------
+// lane-per-edge path (pgd_ell.cuh): layout construction and launches
+// ------------------------------------------------------------------------------------------
+static int ell_pick_G(int max_ns) {
+    int G = 1;
+    while (G * 32 < max_ns) G <<= 1;
+    return G;
+}
+
+// Tile directory + the iteration-invariant index arrays in ELL order; built once per incidence.
+static int ell_build(desc_b200_handle* h) {
+    if (h->ell_G) return DESC_B200_OK;
+    const int G = ell_pick_G(std::max(h->max_ns, 1));
+    if (G > 32 || !h->rk_i) return DESC_B200_ERR_LIMIT;
+    cudaStream_t st = h->stream;
+    const int TE = 32 / G;
+    const int nv = h->v_end - h->v_begin;
+    std::vector<int> vtile(nv + 1, 0), te0, tcnt;
+    for (int v = h->v_begin; v < h->v_end; v++) {
+        vtile[v - h->v_begin] = (int)te0.size();
+        for (int e = h->h_estart[v]; e < h->h_estart[v + 1]; e += TE) {
+            te0.push_back(e);
+            tcnt.push_back(std::min(TE, h->h_estart[v + 1] - e));
+        }
+    }
+    vtile[nv] = (int)te0.size();
+    const int nt = (int)te0.size();
+    int *d_te0 = nullptr, *d_tcnt = nullptr, *d_sizes = nullptr;
+    int64_t* d_tbase = nullptr;
+    CUDA_TRY(cudaMalloc(&h->ell_vtile, (size_t)(nv + 1) * sizeof(int)));
+    CUDA_TRY(cudaMemcpyAsync(h->ell_vtile, vtile.data(), (size_t)(nv + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMalloc(&d_te0, (size_t)std::max(nt, 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_tcnt, (size_t)std::max(nt, 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_sizes, (size_t)std::max(nt, 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&d_tbase, (size_t)(nt + 1) * sizeof(int64_t)));
+    CUDA_TRY(cudaMalloc(&h->ell_tiles, (size_t)std::max(nt, 1) * sizeof(int4)));
+    int64_t total = 0;
+    if (nt > 0) {
+        CUDA_TRY(cudaMemcpyAsync(d_te0, te0.data(), (size_t)nt * sizeof(int), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_tcnt, tcnt.data(), (size_t)nt * sizeof(int), cudaMemcpyHostToDevice, st));
+        k_ell_steps<<<(nt + 255) / 256, 256, 0, st>>>(d_te0, d_tcnt, nt, h->rowptr, G, d_sizes);
+        KERNEL_CHECK(h);
+        DESC_TRY(desc_exclusive_scan_i64(h, d_sizes, d_tbase, nt));
+        CUDA_TRY(cudaMemcpyAsync(&total, d_tbase + nt, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        k_ell_tiles<<<(nt + 255) / 256, 256, 0, st>>>(d_te0, d_sizes, d_tbase, nt, h->ell_tiles);
+        KERNEL_CHECK(h);
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    // d_tcnt is kept inside the permutation launches below only; free the rest
+    h->ell_ntiles = nt;
+    h->ell_size = total;
+    const size_t na = (size_t)std::max<int64_t>(total, 1) + 32;
+    CUDA_TRY(cudaMalloc(&h->ell_d, na * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->ell_rk, na * sizeof(uint16_t)));
+    CUDA_TRY(cudaMalloc(&h->ell_pj, na * sizeof(uint32_t)));
+    for (int b = 0; b < 2; b++) {
+        CUDA_TRY(cudaMalloc(&h->ell_w[b], na * sizeof(double)));
+        CUDA_TRY(cudaMemsetAsync(h->ell_w[b], 0, na * sizeof(double), st));
+    }
+    if (nt > 0) {
+        k_ell_permute<1><<<DESC_SMS * 8, 256, 0, st>>>(h->ell_tiles, d_tcnt, nt, G, h->rowptr, h->slot_base, h->rk_i, h->pk_jk,
+                                                      nullptr, h->ell_rk, h->ell_pj, nullptr, nullptr, nullptr);
+        KERNEL_CHECK(h);
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaFree(d_te0));
+    CUDA_TRY(cudaFree(d_sizes));
+    CUDA_TRY(cudaFree(d_tbase));
+    h->ell_tcnt = d_tcnt;
+    h->ell_G = G;
+    h->ell_have_d = false;
+    return DESC_B200_OK;
+}
+
+template <int G, int EPL, int RULE, int MODE>
+static int launch_ell_t(desc_b200_handle* h, const EllArgs& ea, int nv) {
+    const size_t smem = ell_smem_bytes(ea.tstride, ea.max_ns);
+    if (smem > 200 * 1024) return DESC_B200_ERR_LIMIT;
+    CUDA_TRY(cudaFuncSetAttribute(k_pgd_ell<G, EPL, RULE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_pgd_ell<G, EPL, RULE, MODE><<<nv, ELL_TB, smem, h->stream>>>(ea);
+    KERNEL_CHECK(h);
+    return DESC_B200_OK;
+}
+
+template <int RULE, int MODE>
+static int launch_ell(desc_b200_handle* h, const EllArgs& ea) {
+    const int nv = h->v_end - h->v_begin;
+    if (nv <= 0) return DESC_B200_OK;
+    switch (h->ell_G) {
+        case 1:
+            if (h->max_ns <= 8) return launch_ell_t<1, 8, RULE, MODE>(h, ea, nv);
+            if (h->max_ns <= 16) return launch_ell_t<1, 16, RULE, MODE>(h, ea, nv);
+            return launch_ell_t<1, 32, RULE, MODE>(h, ea, nv);
+        case 2: return launch_ell_t<2, 32, RULE, MODE>(h, ea, nv);
+        case 4: return launch_ell_t<4, 32, RULE, MODE>(h, ea, nv);
+        case 8: return launch_ell_t<8, 32, RULE, MODE>(h, ea, nv);
+        case 16: return launch_ell_t<16, 32, RULE, MODE>(h, ea, nv);
+        case 32: return launch_ell_t<32, 32, RULE, MODE>(h, ea, nv);
+    }
+    return DESC_B200_ERR_LIMIT;
+}
+
 // step size of call number t (1-based count of GetStep calls on the rule object)
 static double step_size(const desc_b200_step_rule* r, int64_t t) {
     switch (r->kind) {
@@ -803,6 +906,187 @@ static double step_size(const desc_b200_step_rule* r, int64_t t) {
             if (r->strategy == 0) return r->lr;
             return 100.0 * (r->lr / (std::trunc((double)t / r->decay_interval) + 1.0));
     }
+}
+
+// The lane-per-edge path: state 0, the iterations with the reference's lagged early stop, the objective of the
+// last state; same bookkeeping kernels and history layout as the other paths.
+static int desc_pgd_ell(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int* iters_run) {
+    cudaStream_t st = h->stream;
+    const int64_t m = h->m;
+    const int64_t nacc = 2 * m + 2;
+    const bool adam = rule->kind == 2 && rule->strategy == 0;
+    DESC_TRY(ell_build(h));
+    const int nt = h->ell_ntiles;
+    if (!h->ell_have_d && nt > 0) {
+        k_ell_permute<2><<<DESC_SMS * 8, 256, 0, st>>>(h->ell_tiles, h->ell_tcnt, nt, h->ell_G, h->rowptr, h->slot_base, nullptr,
+                                                      nullptr, h->S0, nullptr, nullptr, h->ell_d, nullptr, nullptr);
+        KERNEL_CHECK(h);
+    }
+    h->ell_have_d = true;
+    if (adam) {
+        const size_t nb = ((size_t)std::max<int64_t>(h->ell_size, 1) + 32) * sizeof(double);
+        const bool fresh = !h->ell_adam_m;
+        if (!h->ell_adam_m) CUDA_TRY(cudaMalloc(&h->ell_adam_m, nb));
+        if (!h->ell_adam_v) CUDA_TRY(cudaMalloc(&h->ell_adam_v, nb));
+        if (rule->t > 0 && (fresh || !h->adam_valid || h->adam_layout != 1)) {
+            desc_set_error("HybridGradient rule with t=%lld > 0, but this handle holds no Adam moments that continue it "
+                           "(new handle, rebuilt incidence, or a run that was stopped early): HybridGradient.m:24-27 "
+                           "zeroes m_t / v_t only at t == 0", (long long)rule->t);
+            return DESC_B200_ERR_STATE;
+        }
+        if (rule->t == 0) {  // HybridGradient.m:24-27: state is zeroed on the first call only
+            CUDA_TRY(cudaMemsetAsync(h->ell_adam_m, 0, nb, st));
+            CUDA_TRY(cudaMemsetAsync(h->ell_adam_v, 0, nb, st));
+        }
+        h->adam_layout = 1;
+        h->adam_valid = false;   // becomes valid again when this run ends without an early stop
+    }
+    const int nv = h->v_end - h->v_begin;
+    EllArgs ea;
+    PgdArgs& a = ea.p;
+    a.rowptr = h->rowptr;
+    a.pk_jk = nullptr;
+    a.pk_ki = nullptr;
+    a.S0 = nullptr;
+    a.adam_m = h->ell_adam_m;
+    a.adam_v = h->ell_adam_v;
+    a.ctrl = h->d_ctrl;
+    a.e0 = h->e_begin;
+    a.e1 = h->e_end;
+    a.slot_base = h->slot_base;
+    a.m = m;
+    a.beta1 = rule->beta_1;
+    a.beta2 = rule->beta_2;
+    a.corr1 = a.corr2 = 1.0;
+    a.lr = 0.0;
+    ea.tiles = h->ell_tiles;
+    ea.vtile = h->ell_vtile;
+    ea.d = h->ell_d;
+    ea.rk = h->ell_rk;
+    ea.pj = h->ell_pj;
+    ea.rowstart = h->rowstart;
+    ea.adj_nbr = h->adj_nbr;
+    ea.adj_eid = h->adj_eid;
+    ea.estart = h->estart;
+    ea.v0 = h->v_begin;
+    ea.tstride = (h->maxdeg + 1 + 3) & ~3;
+    ea.max_ns = std::max(h->max_ns, 1);
+    ea.partial = h->pgd_partial;
+    const int launches0 = h->launches;
+
+    // ---- state 0 (DESC.m:148-157)
+    CUDA_TRY(cudaMemsetAsync(h->acc[0], 0, nacc * sizeof(double), st));
+    a.w_cur = nullptr;
+    a.w_next = h->ell_w[0];
+    a.S_cur = nullptr;
+    a.S_next = h->S[0];
+    a.acc_cur = nullptr;
+    a.acc_next = h->acc[0];
+    if (nt > 0) DESC_TRY((launch_ell<0, 1>(h, ea)));
+    if (h->world > 1) {
+        DESC_TRY(desc_allgather_ranges(h, h->S[0], sizeof(double), h->shard_edges));
+        DESC_TRY(desc_reduce_to_owners(h, h->acc[0], 2, h->shard_edges, 2, true));
+    }
+
+    std::vector<cudaEvent_t>& evs = h->iter_events;
+    while ((int)evs.size() < 5 * std::min(iters, 512)) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        evs.push_back(e);
+    }
+    int t_done = 0;
+    bool stopped = false;
+    const int check_every = h->diag_on ? 1 : 8;
+    for (int t = 1; t <= iters && !stopped; t++) {
+        const int cur = (t - 1) & 1, nxt = t & 1;
+        CUDA_TRY(cudaMemsetAsync(h->acc[nxt], 0, nacc * sizeof(double), st));
+        a.w_cur = h->ell_w[cur];
+        a.w_next = h->ell_w[nxt];
+        a.S_cur = h->S[cur];
+        a.S_next = h->S[nxt];
+        a.acc_cur = h->acc[cur];
+        a.acc_next = h->acc[nxt];
+        const int64_t tcall = rule->t + t;
+        a.lr = step_size(rule, tcall);
+        if (adam) {
+            a.corr1 = 1.0 - std::pow(rule->beta_1, (double)tcall);
+            a.corr2 = 1.0 - std::pow(rule->beta_2, (double)tcall);
+        }
+        const bool timed = t <= 512;
+        if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1)], st));
+        if (nt > 0) {
+            if (adam)
+                DESC_TRY((launch_ell<1, 0>(h, ea)));
+            else
+                DESC_TRY((launch_ell<0, 0>(h, ea)));
+        }
+        if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 1], st));
+        k_pgd_partials<<<1, 256, 0, st>>>(h->pgd_partial, nt > 0 ? nv : 0, h->d_ctrl, h->acc[nxt] + 2 * m);
+        KERNEL_CHECK(h);
+        if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 3], st));
+        if (h->world > 1) {
+            DESC_TRY(desc_allgather_ranges(h, h->S[nxt], sizeof(double), h->shard_edges));
+            DESC_TRY(desc_reduce_to_owners(h, h->acc[nxt], 2, h->shard_edges, 2, true));
+        }
+        if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 4], st));
+        if (h->diag_on) DESC_TRY(desc_diag_record(h, t, h->S[nxt]));
+        k_pgd_finalize<<<1, 1, 0, st>>>(h->acc[nxt] + 2 * m, t, 0, m, 1e-5, 30, h->d_hist, h->d_ctrl, h->d_ctrl_f);
+        KERNEL_CHECK(h);
+        t_done = t;
+        if (t % check_every == 0 || t == iters) {
+            CUDA_TRY(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            stopped = h->h_ctrl[0] != 0;
+        }
+    }
+    int final_iter = 0;
+    if (stopped) {
+        final_iter = h->h_ctrl[1];
+    } else if (iters > 0) {
+        const int cur = iters & 1, nxt = (iters + 1) & 1;
+        CUDA_TRY(cudaMemsetAsync(h->acc[nxt] + 2 * m, 0, 2 * sizeof(double), st));
+        a.w_cur = h->ell_w[cur];
+        a.S_cur = h->S[cur];
+        a.acc_cur = h->acc[cur];
+        a.acc_next = h->acc[nxt];
+        if (nt > 0) DESC_TRY((launch_ell<0, 2>(h, ea)));
+        k_pgd_partials<<<1, 256, 0, st>>>(h->pgd_partial, nt > 0 ? nv : 0, h->d_ctrl, h->acc[nxt] + 2 * m);
+        KERNEL_CHECK(h);
+        if (h->world > 1) DESC_TRY(desc_allreduce_sum(h, h->acc[nxt] + 2 * m, 2));
+        k_pgd_finalize<<<1, 1, 0, st>>>(h->acc[nxt] + 2 * m, iters, 1, m, 1e-5, 30, h->d_hist, h->d_ctrl, h->d_ctrl_f);
+        KERNEL_CHECK(h);
+        final_iter = iters;
+    }
+    // the weights of the final state back in the reference's slot order (getters, later stages)
+    if (nt > 0) {
+        k_ell_permute<4><<<DESC_SMS * 8, 256, 0, st>>>(h->ell_tiles, h->ell_tcnt, nt, h->ell_G, h->rowptr, h->slot_base, nullptr,
+                                                      nullptr, nullptr, nullptr, nullptr, nullptr, h->ell_w[final_iter & 1],
+                                                      h->w[final_iter & 1]);
+        KERNEL_CHECK(h);
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    h->final_buf = final_iter & 1;
+    h->have_pgd = true;
+    *iters_run = final_iter;
+    rule->t += final_iter;
+    if (adam) h->adam_valid = !stopped;   // a stopped run has advanced the moments one launch past the reported state
+    double s1 = 0.0, sc = 0.0;
+    int cnt = 0;
+    for (int t = 1; t <= std::min(std::min(t_done, 512), std::max(final_iter, 1)); t++) {
+        float a1 = 0.f, ar = 0.f;
+        cudaEvent_t* e = &evs[5 * (t - 1)];
+        if (cudaEventElapsedTime(&a1, e[0], e[1]) == cudaSuccess && cudaEventElapsedTime(&ar, e[3], e[4]) == cudaSuccess) {
+            s1 += a1;
+            sc += ar;
+            cnt++;
+        }
+    }
+    h->tm.pgd_pass1_ms = cnt > 0 ? s1 / cnt : 0.0;
+    h->tm.pgd_pass2_ms = 0.0;
+    h->tm.pgd_comm_ms = cnt > 0 ? sc / cnt : 0.0;
+    h->tm.pgd_iter_ms = h->tm.pgd_pass1_ms;
+    h->tm.pgd_launches = h->launches - launches0;
+    return DESC_B200_OK;
 }
 
 int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int* iters_run) {
@@ -842,14 +1126,31 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
         CUDA_TRY(cudaMalloc(&h->d_hist, (size_t)2 * (iters + 1) * sizeof(double)));
         h->hist_cap = iters + 1;
     }
-    if (adam) {
+    // DESC_B200_PGD_PATH = stream (default) | ell | blocked | generic
+    bool use_ell = false;
+    {
+        const char* force = getenv("DESC_B200_PGD_PATH");
+        const bool want_ell = force && strcmp(force, "ell") == 0;
+        use_ell = want_ell && blocked && ell_pick_G(std::max(h->max_ns, 1)) <= 32 &&
+                  ell_smem_bytes((h->maxdeg + 1 + 3) & ~3, std::max(h->max_ns, 1)) <= 200 * 1024;
+    }
+    if (adam && !use_ell) {
         const size_t nb = (size_t)std::max<int64_t>(h->n_slots, 1) * sizeof(double);
+        const bool fresh = !h->adam_m;
         if (!h->adam_m) CUDA_TRY(cudaMalloc(&h->adam_m, nb));
         if (!h->adam_v) CUDA_TRY(cudaMalloc(&h->adam_v, nb));
+        if (rule->t > 0 && (fresh || !h->adam_valid || h->adam_layout != 0)) {
+            desc_set_error("HybridGradient rule with t=%lld > 0, but this handle holds no Adam moments that continue it "
+                           "(new handle, rebuilt incidence, or a run that was stopped early): HybridGradient.m:24-27 "
+                           "zeroes m_t / v_t only at t == 0", (long long)rule->t);
+            return DESC_B200_ERR_STATE;
+        }
         if (rule->t == 0) {  // HybridGradient.m:24-27: state is zeroed on the first call only
             CUDA_TRY(cudaMemsetAsync(h->adam_m, 0, nb, st));
             CUDA_TRY(cudaMemsetAsync(h->adam_v, 0, nb, st));
         }
+        h->adam_layout = 0;
+        h->adam_valid = false;
     }
     CUDA_TRY(cudaMemsetAsync(h->d_ctrl, 0, 4 * sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(h->d_ctrl_f, 0, 2 * sizeof(double), st));
@@ -861,6 +1162,7 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
         k_fill_double<<<gb, 256, 0, st>>>(h->S[1], m, 1.0);
         KERNEL_CHECK(h);
     }
+    if (use_ell) return desc_pgd_ell(h, iters, rule, iters_run);
     PgdArgs a;
     a.rowptr = h->rowptr;
     a.pk_jk = h->pk_jk;
@@ -1037,6 +1339,7 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
     h->have_pgd = true;
     *iters_run = final_iter;
     rule->t += final_iter;
+    if (adam) h->adam_valid = !stopped;   // a stopped run has advanced the moments one launch past the reported state
     // mean durations over the iterations that did real work: kernels of pass 1 / pass 2, collectives
     double s1 = 0.0, s2 = 0.0, sc = 0.0;
     int cnt = 0;

@@ -113,19 +113,31 @@ static inline int32_t edge_of(const int64_t* rowstart, const int32_t* nbr, const
     return eid[lo];
 }
 
-typedef struct {
-    uint64_t key;
-    int32_t k;
-} keyed;
-static int cmp_keyed(const void* a, const void* b) {
-    const keyed* x = (const keyed*)a;
-    const keyed* y = (const keyed*)b;
-    if (x->key != y->key) return x->key < y->key ? -1 : 1;
-    return (x->k > y->k) - (x->k < y->k);
-}
-static int cmp_i32(const void* a, const void* b) {
-    const int32_t x = *(const int32_t*)a, y = *(const int32_t*)b;
-    return (x > y) - (x < y);
+/* k-th smallest (0-based) of a[0..n) by Hoare quickselect; permutes a */
+static uint64_t kth_smallest(uint64_t* a, int n, int k) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const uint64_t piv = a[lo + ((hi - lo) >> 1)];
+        int i = lo, j = hi;
+        while (i <= j) {
+            while (a[i] < piv) i++;
+            while (a[j] > piv) j--;
+            if (i <= j) {
+                const uint64_t t = a[i];
+                a[i] = a[j];
+                a[j] = t;
+                i++;
+                j--;
+            }
+        }
+        if (k <= j)
+            hi = j;
+        else if (k >= i)
+            lo = i;
+        else
+            break;
+    }
+    return a[k];
 }
 
 /* ---- A3: slot lists (DESC.m:56-96).  rowptr_all (m+1) = exclusive scan of min(codeg, n_sample) over ALL edges.
@@ -140,7 +152,9 @@ void desc_c_fill(int64_t n, int64_t m, const int32_t* ei, const int32_t* ej, con
         if (codeg[e] > maxc) maxc = codeg[e];
 #pragma omp parallel
     {
-        keyed* cand = (keyed*)malloc(sizeof(keyed) * (size_t)maxc);
+        int32_t* cand = (int32_t*)malloc(sizeof(int32_t) * (size_t)maxc);
+        uint64_t* key = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)maxc);
+        uint64_t* tmp = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)maxc);
         int32_t* keep = (int32_t*)malloc(sizeof(int32_t) * (size_t)maxc);
 #pragma omp for schedule(dynamic, 256)
         for (int64_t e = 0; e < m; e++) {
@@ -155,19 +169,30 @@ void desc_c_fill(int64_t n, int64_t m, const int32_t* ei, const int32_t* ej, con
                 while (x) {
                     const int bit = __builtin_ctzll(x);
                     x &= x - 1;
-                    cand[cnt].k = (int32_t)(w * 64 + bit);
-                    cnt++;
+                    cand[cnt++] = (int32_t)(w * 64 + bit);
                 }
             }
             int ns = c;
-            if (c > n_sample) {                                /* DESC.m:83-85 with the shared key sampler */
-                for (int q = 0; q < c; q++) cand[q].key = desc_key(seed, (uint64_t)e, (uint64_t)cand[q].k);
-                qsort(cand, (size_t)c, sizeof(keyed), cmp_keyed);
-                ns = n_sample;
-                for (int q = 0; q < ns; q++) keep[q] = cand[q].k;
-                qsort(keep, (size_t)ns, sizeof(int32_t), cmp_i32);
+            if (c > n_sample) {
+                /* DESC.m:83-85 with the shared key sampler: keep the n_sample smallest (key, apex) pairs, in
+                   ascending apex order.  Threshold = n_sample-th smallest key; ties (never seen with 64-bit keys,
+                   handled anyway) go to the smallest apices, which is the (key, apex) order. */
+                for (int q = 0; q < c; q++) tmp[q] = key[q] = desc_key(seed, (uint64_t)e, (uint64_t)cand[q]);
+                const uint64_t thr = kth_smallest(tmp, c, n_sample - 1);
+                int below = 0;
+                for (int q = 0; q < c; q++) below += key[q] < thr;
+                int ties = n_sample - below;
+                ns = 0;
+                for (int q = 0; q < c; q++) {
+                    if (key[q] < thr)
+                        keep[ns++] = cand[q];
+                    else if (key[q] == thr && ties > 0) {
+                        keep[ns++] = cand[q];
+                        ties--;
+                    }
+                }
             } else {
-                for (int q = 0; q < ns; q++) keep[q] = cand[q].k;
+                for (int q = 0; q < ns; q++) keep[q] = cand[q];
             }
             const int64_t r0 = rowptr_all[e];
             for (int q = 0; q < ns; q++) {
@@ -178,6 +203,8 @@ void desc_c_fill(int64_t n, int64_t m, const int32_t* ei, const int32_t* ej, con
             }
         }
         free(cand);
+        free(key);
+        free(tmp);
         free(keep);
     }
 }

@@ -363,8 +363,11 @@ def test_generic_atomic_path_still_matches_oracle(monkeypatch):
         assert_solution_close(c, o)
 
 
-def test_vertex_blocked_path_is_bit_reproducible():
-    """no atomics in the default path: two runs give bit-identical S_vec, w and history"""
+@pytest.mark.parametrize("path", ["ell", "stream"])
+def test_default_paths_are_bit_reproducible(monkeypatch, path):
+    """lane-per-edge path: partner sums are integer (fixed-point) reductions; streamed path: no atomics at all.
+    Two runs give bit-identical S_vec, w and history"""
+    monkeypatch.setenv("DESC_B200_PGD_PATH", path)
     mo = O.uniform_topology(220, 0.4, 0.2, 0.1, "uniform", rng=32)
     a = run_cuda(mo["Ind"], mo["RijMat"], desc_b200.ConstantStepSize(0.01), 50, seed=1, gcw=False)
     b = run_cuda(mo["Ind"], mo["RijMat"], desc_b200.ConstantStepSize(0.01), 50, seed=1, gcw=False)
@@ -385,6 +388,54 @@ def test_blocked_direct_load_path_still_matches_oracle(monkeypatch):
         assert_solution_close(c, o)
 
 
+@pytest.mark.parametrize("ns", [0, 6, 12, 45, 100])
+@pytest.mark.parametrize("rule", ["const", "adam"])
+def test_lane_per_edge_path_slot_list_lengths(monkeypatch, ns, rule):
+    """k_pgd_ell (experimental single-kernel path): 1, 2 and 4 lanes per edge, 8 / 16 / 32 slots per lane, constant step and Adam,
+    against the oracle"""
+    monkeypatch.setenv("DESC_B200_PGD_PATH", "ell")
+    mo = O.uniform_topology(240, 0.65, 0.2, 0.1, "uniform", rng=34)
+    if rule == "const":
+        rc, ro = desc_b200.ConstantStepSize(0.05), O.ConstantStepSize(0.05)
+    else:
+        rc, ro = desc_b200.HybridGradient(0.002, 0.9, 0.999, 25), O.HybridGradient(0.002, 0.9, 0.999, 25)
+    c = run_cuda(mo["Ind"], mo["RijMat"], rc, 20, n_sample=ns, seed=4, gcw=False)
+    o = run_oracle(mo["Ind"], mo["RijMat"], ro, 20, n_sample=(None if ns == 0 else ns), seed=4, gcw=False)
+    assert_incidence_equal(c, o["inc"])
+    assert_solution_close(c, o)
+
+
+def test_hybrid_gradient_rule_reuse_on_new_handle_is_rejected():
+    """HybridGradient.m:24-27 zeroes the moments only at t == 0: a rule object that has already stepped cannot be
+    continued on a handle that does not hold its moments; a fresh rule on the same handle works, and a
+    second call with the advanced rule on the SAME handle continues the first"""
+    mo = O.uniform_topology(120, 0.5, 0.2, 0.1, "uniform", rng=37)
+    rule = desc_b200.HybridGradient(0.002, 0.9, 0.999, 25)
+    orule = O.HybridGradient(0.002, 0.9, 0.999, 25)
+    with desc_b200.Solver(mo["Ind"], mo["RijMat"]) as s:
+        s.build_incidence(seed=2)
+        s.cycle_inconsistency()
+        s.pgd(6, rule)
+        S_second, _, _ = s.pgd(4, rule)                  # same handle: the rule's t and moments continue, weights restart
+        assert rule.t == 10
+    inc = O.build_incidence(mo["Ind"], seed=2)
+    S0 = O.cycle_inconsistency(inc, mo["RijMat"])
+    two = O.HybridGradient(0.002, 0.9, 0.999, 25)
+    O.pgd(inc, S0, 6, two)
+    oS_second, _, _ = O.pgd(inc, S0, 4, two)
+    assert rel_err(S_second, oS_second, floor=1e-12) <= RTOL
+    with desc_b200.Solver(mo["Ind"], mo["RijMat"]) as s:
+        s.build_incidence(seed=2)
+        s.cycle_inconsistency()
+        with pytest.raises(desc_b200.DescError) as e:
+            s.pgd(10, rule)
+        assert e.value.code == _lib.ERR_STATE
+        fresh = desc_b200.HybridGradient(0.002, 0.9, 0.999, 25)
+        S, _, _ = s.pgd(10, fresh)
+    oS, _, _ = O.pgd(inc, S0, 10, orule)
+    assert rel_err(S, oS, floor=1e-12) <= RTOL
+
+
 _ORACLE_CACHE = {}
 
 
@@ -403,6 +454,7 @@ def _cached_case(n, p, rng, lr, iters, ns, seed):
 def test_streamed_path_launch_shapes_and_slot_list_lengths(monkeypatch, shape, ns):
     """every compiled (slots per lane, compute warps, scatter warps) shape of the TMA-streamed kernel, with
     slot lists of <=32, <=64 and <=128 entries (4..16 or 8..32 lanes per edge), against the oracle"""
+    monkeypatch.setenv("DESC_B200_PGD_PATH", "stream")
     monkeypatch.setenv("DESC_B200_ST", shape)
     mo, o = _cached_case(240, 0.65, 34, 0.05, 20, ns, 4)
     c = run_cuda(mo["Ind"], mo["RijMat"], desc_b200.ConstantStepSize(0.05), 20, n_sample=ns, seed=4, gcw=False)
@@ -411,8 +463,10 @@ def test_streamed_path_launch_shapes_and_slot_list_lengths(monkeypatch, shape, n
     assert_solution_close(c, o)
 
 
-def test_streamed_path_slot_lists_up_to_256():
-    """all triangles of a dense graph (co-degrees above 128): the widest lanes-per-edge instantiation"""
+@pytest.mark.parametrize("path", ["stream", "ell"])
+def test_slot_lists_up_to_256(monkeypatch, path):
+    """all triangles of a dense graph (co-degrees above 128): the widest lanes-per-edge instantiations"""
+    monkeypatch.setenv("DESC_B200_PGD_PATH", path)
     mo, o = _cached_case(380, 0.62, 36, 0.05, 6, -1, 4)
     c = run_cuda(mo["Ind"], mo["RijMat"], desc_b200.ConstantStepSize(0.05), 6, n_sample=-1, seed=4, gcw=False)
     assert 128 < c["info"]["max_slots_per_edge"] <= 256
@@ -423,6 +477,7 @@ def test_streamed_path_slot_lists_up_to_256():
 
 def test_second_pass_tma_variant_matches_oracle(monkeypatch):
     """DESC_B200_PASSB=tma: the pass over larger endpoints fed by per-edge bulk copies"""
+    monkeypatch.setenv("DESC_B200_PGD_PATH", "stream")
     monkeypatch.setenv("DESC_B200_PASSB", "tma")
     mo = O.uniform_topology(200, 0.5, 0.2, 0.1, "uniform", rng=35)
     for ns in (0, 40):
