@@ -1,27 +1,37 @@
 #!/usr/bin/env python
 """bench.py -- DESC solve throughput on B200 (metric of BASELINE.json), one JSON line on stdout.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg4|cfg2|cfg3|cfg3sc|cfg5]
 
 A "step" is one complete DESC_init-equivalent solve (DESC.m:14-263 + GCW.m) of the workload:
 CSR incidence build + cycle inconsistencies + PGD (iterations actually run) + GCW recovery.
-Workload (configs[3] of BASELINE.json, the configuration the metric is quoted on; it fits one
-GPU): Uniform_Topology(n=10000, p=0.1, q=0.2, sigma=0.1, 'uniform'), params = {iters=100,
-Gradient=ConstantStepSize(0.01)} (Demo/compare_algorithms.m:39-45), reference sampling rule.
+Default workload = configs[3] of BASELINE.json (the configuration the metric is quoted on; it fits one GPU):
+Uniform_Topology(n=10000, p=0.1, q=0.2, sigma=0.1, 'uniform'), params = {iters=100, Gradient=ConstantStepSize(0.01)}
+(Demo/compare_algorithms.m:39-45), reference sampling rule.  Inputs are drawn by the library's own device generators
+(csrc/gen.cu, counter-based: every rank draws the identical graph, nothing is broadcast).
 
 value  = 3-cycle evaluations per second over the whole step = m_cycle * iters_run / step time,
          inputs (Ind, RijMat) already resident in HBM; N>1 shards the same problem ("strong").
 e2e    = the same through the reference-style call with HOST (pinned) buffers: H2D of Ind/RijMat
          and D2H of S_vec / R_est / history inside the timed region.
-roofline = one PGD iteration = its two kernels (k_pgd_stream: update pass over smaller endpoints,
-         k_pgd_passb: table pass over larger endpoints): algorithmic bytes (40*m_cycle + 12*m_pos + 8*m,
-         SURVEY 8d) / mean duration of the pair (CUDA events on the launching stream around each
-         kernel) vs the measured HBM peak.  `traffic` = DRAM bytes of the pair from the committed ncu
-         capture (profiles/), valid for the default workload on one GPU.
-cpu_baseline = the CPU restatement (oracle/) timed on this box's host cores on a bounded sample.
+roofline = one PGD iteration (its two kernels): algorithmic bytes (40*m_cycle + 12*m_pos + 8*m) / mean
+         duration of the pair (CUDA events on the launching stream around each kernel) vs the measured HBM peak.
+         `traffic` = DRAM bytes of the pair from the committed ncu capture (profiles/r02_pgd_traffic.json), used only
+         when the sha1 of the kernel sources it was captured on equals the current sources (else null + reason).
+         `stages` = the same arithmetic for the one-off kernels (incidence build, d_ijk, one GCW SpMV).
+cpu_baseline / --impl reference = the C/OpenMP restatement of the reference (oracle/desc_full.c + desc_pgd.c, every
+         stage threaded, thread count = the cores this process may run on, set explicitly) on a graph of the
+         workload's own family and co-degree regime: the workload's graph itself when the time budget allows,
+         otherwise the largest smaller member of the family that fits; its true n / m / m_cycle are in the line.
+         All stages run at that size; the PGD loop is timed over k iterations and the whole-solve time is
+         fixed stages + iters * per-iteration time (every iteration does the same arithmetic), stated in `sample`.
+parity = (N > 1) the N-rank result against a 1-rank solve of the same inputs on rank 0: max |dS_vec|, iters_run,
+         mean rotation angle after gauge alignment.
 """
 import argparse
+import hashlib
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -32,16 +42,30 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    "cfg4": dict(n=10000, p=0.1, q=0.2, sigma=0.1, model="uniform", iters=100, lr=0.01,
+    "cfg4": dict(kind="uniform", n=10000, p=0.1, q=0.2, sigma=0.1, model="uniform", iters=100, lr=0.01, n_sample=0,
                  name="Uniform_Topology n=10000 p=0.1 q=0.2 sigma=0.1 uniform, iters=100 ConstantStepSize(0.01)"),
-    "cfg2": dict(n=1000, p=0.5, q=0.3, sigma=0.1, model="uniform", iters=100, lr=0.01,
+    "cfg2": dict(kind="uniform", n=1000, p=0.5, q=0.3, sigma=0.1, model="uniform", iters=100, lr=0.01, n_sample=0,
                  name="Uniform_Topology n=1000 p=0.5 q=0.3 sigma=0.1 uniform, iters=100 ConstantStepSize(0.01)"),
-    "small": dict(n=2000, p=0.1, q=0.2, sigma=0.1, model="uniform", iters=100, lr=0.01,
+    # configs[2]: BASELINE.json fixes only n and the corruption type; the rest is SURVEY 8d's proposal, recorded here
+    "cfg3": dict(kind="nonuniform", n=2000, p=0.5, p_node_crpt=0.3, p_edge_crpt=0.5, sigma=0.1, sigma_out=0.1,
+                 crpt_type="adv", iters=100, lr=0.01, n_sample=0,
+                 name="Nonuniform_Topology n=2000 p=0.5 p_node_crpt=0.3 p_edge_crpt=0.5 sigma_in=0.1 sigma_out=0.1 adv, "
+                      "iters=100 ConstantStepSize(0.01)"),
+    "cfg3sc": dict(kind="nonuniform", n=2000, p=0.5, p_node_crpt=0.3, p_edge_crpt=0.5, sigma=0.1, sigma_out=0.1,
+                   crpt_type="self-consistent", iters=100, lr=0.01, n_sample=0,
+                   name="Nonuniform_Topology n=2000 p=0.5 p_node_crpt=0.3 p_edge_crpt=0.5 sigma_in=0.1 sigma_out=0.1 "
+                        "self-consistent, iters=100 ConstantStepSize(0.01)"),
+    # configs[4]: SfM-shaped ring (no reference generator), the reference's large-scale settings compare_algorithms.m:2-5
+    "cfg5": dict(kind="ring", n=50000, deg=100, window=75, q=0.2, sigma=0.05, iters=30, lr=1.0, n_sample=50,
+                 name="Ring_Topology (SfM-shaped) n=50000 mean degree 100 window 75 q=0.2 sigma=0.05, 50 sampled 3-cycles "
+                      "per edge, iters=30 ConstantStepSize(1)"),
+    "small": dict(kind="uniform", n=2000, p=0.1, q=0.2, sigma=0.1, model="uniform", iters=100, lr=0.01, n_sample=0,
                   name="Uniform_Topology n=2000 p=0.1 q=0.2 sigma=0.1 uniform, iters=100 ConstantStepSize(0.01)"),
 }
-NCU_TRAFFIC_CFG4 = 9005426000   # k_pgd_stream 5.654e9 + k_pgd_passb 3.351e9 (profiles/r01_v7_ncu_full_summary.txt)
 METRIC = "DESC 3-cycle evals/s (whole solve: incidence + d_ijk + PGD + GCW)"
 UNIT = "evals/s"
+PGD_SOURCES = ["desc_b200/csrc/pgd.cu", "desc_b200/csrc/pgd_stream.cuh", "desc_b200/csrc/pgd_passb.cuh"]
+TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r02_pgd_traffic.json")
 
 
 def measured_peak():
@@ -52,6 +76,25 @@ def measured_peak():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def captured_traffic(workload, world):
+    """DRAM bytes of one PGD iteration from the committed ncu capture, or (None, reason)."""
+    if workload != "cfg4" or world != 1:
+        return None, "the capture is of cfg4 on one GPU"
+    if not os.path.exists(TRAFFIC_JSON):
+        return None, "no capture committed"
+    try:
+        j = json.load(open(TRAFFIC_JSON))
+        sha = hashlib.sha1()
+        for s in j["sources"]:
+            sha.update(open(os.path.join(ROOT, s), "rb").read())
+        if sha.hexdigest() != j["sources_sha1"]:
+            return None, "kernel sources changed since the capture (%s)" % j.get("report")
+        d = j["dram_bytes_per_launch"]
+        return sum(v for k, v in d.items() if "k_pgd_stream" in k or "k_pgd_passb" in k), j.get("report")
+    except Exception as e:   # noqa: BLE001
+        return None, "unreadable capture: %s" % e
 
 
 class ClockSampler:
@@ -96,56 +139,160 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# CPU baseline: the oracle port on a bounded sample of the workload
+# CPU arm: the C/OpenMP restatement on the workload's own graph family
 # ------------------------------------------------------------------------------------------
-def cpu_sample(wl, n_sub, iters, seed=0):
-    """CPU restatement of the reference on the workload family at n_sub nodes (same edge density and
-    sampling rule): numpy oracle for the incidence, d_ijk and GCW (1 thread), the C/OpenMP restatement
-    of the PGD loop (oracle/desc_pgd.c, DESC.m:148-261 statement by statement) on all host threads.
-    Returns whole-solve evals/s like `value`, the wall time and a description."""
+# thread-seconds per slot measured on the build container (8 Xeon threads, cfg-4 graph): used only to size the sample
+CPU_COST_FIXED, CPU_COST_ITER = 9.4e-7, 1.2e-7
+_CPU_INPUTS = {}
+
+
+def workload_estimates(wl):
+    """(m, m_cycle) of the workload from its parameters (the CPU arm must not need a GPU to size its sample)"""
+    if wl["kind"] == "ring":
+        m = wl["n"] * wl["deg"] / 2.0
+        p = wl["deg"] / (2.0 * wl["window"])
+        codeg = 1.5 * wl["window"] * p * p          # mean common-neighbour count of a window graph (approximate)
+    else:
+        m = wl["p"] * wl["n"] * (wl["n"] - 1) / 2.0
+        codeg = wl["n"] * wl["p"] ** 2
+    ns = wl["n_sample"] if wl["n_sample"] > 0 else max(math.ceil(codeg / 4.0), 30)
+    return m, m * min(codeg, ns)
+
+
+def cpu_sample_spec(wl, budget_s, threads, k):
+    """the workload's graph itself if its predicted CPU time fits the budget, else the largest smaller member of the
+    same family with the same co-degree regime (uniform / nonuniform: p scaled by sqrt(n/n_sub); ring: same degree
+    and window)"""
+    m, mc = workload_estimates(wl)
+    for div in (1, 2, 4, 6, 8, 12, 16, 24, 32, 64):
+        n_sub = max(200, wl["n"] // div)
+        if wl["kind"] == "ring":
+            frac = n_sub / wl["n"]
+        else:
+            frac = (n_sub / wl["n"]) ** 1.5
+        pred = mc * frac * (CPU_COST_FIXED + CPU_COST_ITER * k) / threads * 1.3 + 1.0
+        if pred <= budget_s or n_sub == 200:
+            spec = dict(wl)
+            spec["n"] = n_sub
+            if wl["kind"] != "ring":
+                spec["p"] = min(0.95, wl["p"] * math.sqrt(wl["n"] / n_sub))
+            spec["same_graph"] = div == 1
+            spec["predicted_s"] = pred
+            return spec
+    return None
+
+
+def cpu_inputs(spec, seed):
+    """host inputs of the sample (not timed): graph of the family + the reference model's rotation distribution"""
+    import numpy as np
+    from oracle import desc_oracle as O
+    key = (spec["kind"], spec["n"], spec.get("p"), seed)
+    if key in _CPU_INPUTS:
+        return _CPU_INPUTS[key]
+    rng = np.random.default_rng(seed)
+    n = spec["n"]
+    if spec["kind"] == "ring":
+        w = spec["window"]
+        p = spec["deg"] / (2.0 * w)
+        rows = []
+        for d in range(1, w + 1):                    # pairs at circular distance d
+            i = np.nonzero(rng.random(n) < p)[0]
+            j = (i + d) % n
+            rows.append(np.stack([np.minimum(i, j), np.maximum(i, j)], axis=1))
+        e = np.unique(np.concatenate(rows), axis=0)
+        ei, ej = e[:, 0], e[:, 1]
+    else:
+        ei_l, ej_l = [], []
+        step = max(1, 20_000_000 // n)
+        for a in range(0, n, step):                  # strictly lower triangle in row blocks (Uniform_Topology.m:29-35)
+            b = min(n, a + step)
+            blk = rng.random((b - a, n)) < spec["p"]
+            r, c = np.nonzero(blk)
+            keep = c < (r + a)
+            ej_l.append(r[keep] + a)
+            ei_l.append(c[keep])
+        ei, ej = np.concatenate(ei_l), np.concatenate(ej_l)
+        o = np.lexsort((ej, ei))
+        ei, ej = ei[o], ej[o]
+    deg = np.bincount(ei, minlength=n) + np.bincount(ej, minlength=n)
+    if (deg == 0).any():
+        raise SystemExit("CPU sample graph has an isolated node; use a larger sample")
+    m = ei.size
+    R = O.proj_so3(rng.standard_normal((n, 3, 3)))
+    Rij = R[ei] @ R[ej].transpose(0, 2, 1)
+    q, sigma = spec.get("q", 0.2), spec["sigma"]
+    corr = rng.random(m) < q
+    Rij[~corr] += sigma * rng.standard_normal((int((~corr).sum()), 3, 3))
+    Rij[corr] = rng.standard_normal((int(corr.sum()), 3, 3))
+    for a in range(0, m, 1_000_000):
+        Rij[a:a + 1_000_000] = O.proj_so3(Rij[a:a + 1_000_000])
+    Ind = np.stack([ei + 1, ej + 1], axis=1).astype(np.float64)
+    out = (Ind, O.to_matlab(Rij))
+    _CPU_INPUTS.clear()
+    _CPU_INPUTS[key] = out
+    return out
+
+
+def cpu_arm(wl, budget_s, seed=0, k=10):
+    """one CPU sample: whole-solve evals/s of the C/OpenMP port, per-stage seconds, and what exactly was run"""
     from oracle import desc_oracle as O
     from oracle import desc_oracle_c as OC
-    threads = OC.max_threads()
-    mo = O.uniform_topology(n_sub, wl["p"], wl["q"], wl["sigma"], wl["model"], rng=seed)
+    threads = OC.host_threads()
+    k = max(1, min(k, wl["iters"]))
+    spec = cpu_sample_spec(wl, budget_s, threads, k)
+    Ind, RijMat = cpu_inputs(spec, seed)
     t0 = time.perf_counter()
-    inc = O.build_incidence(mo["Ind"], n_sample=None, seed=1)
-    S0 = O.cycle_inconsistency(inc, mo["RijMat"])
-    t1 = time.perf_counter()
-    S_vec, hist, iters_run = OC.pgd(inc, S0, iters, O.ConstantStepSize(wl["lr"]), threads=threads)
-    t2 = time.perf_counter()
-    O.gcw(mo["Ind"], mo["RijMat"], S_vec)
-    dt = time.perf_counter() - t0
-    return inc.m_cycle * iters_run / dt, dt, dict(n=n_sub, m=int(inc.m), m_cycle=int(inc.m_cycle), iters=int(iters_run),
-                                                  threads=threads, pgd_s=t2 - t1,
-                                                  pgd_evals_per_s=inc.m_cycle * iters_run / (t2 - t1))
-
-
-CPU_SAMPLE_TEXT = ("CPU restatement of DESC.m:14-263 + GCW.m on the same graph family at n=%d (m=%d, m_cycle=%d), %d PGD "
-                   "iterations: numpy oracle for incidence / d_ijk / GCW (1 thread) + C/OpenMP PGD loop (%d threads, "
-                   "%.2e evals/s in the loop alone); %.1f s")
+    r = OC.DESC_init(Ind, RijMat, dict(iters=k, Gradient=O.ConstantStepSize(wl["lr"])),
+                     n_sample=(wl["n_sample"] or None), seed=1, threads=threads, full=True)
+    wall = time.perf_counter() - t0
+    tm, inc = r["timings"], r["inc"]
+    per_iter = tm["pgd_s"] / max(r["iters_run"], 1)
+    fixed = tm["graph_s"] + tm["build_s"] + tm["cycle_s"] + tm["gcw_s"]
+    solve_s = fixed + per_iter * wl["iters"]
+    value = inc.m_cycle * wl["iters"] / solve_s
+    info = dict(n=int(inc.n), m=int(inc.m), m_cycle=int(inc.m_cycle), n_sample=int(inc.n_sample), threads=threads,
+                same_graph=bool(spec["same_graph"]), pgd_iterations_timed=int(r["iters_run"]),
+                stage_s={k2: round(v, 4) for k2, v in tm.items()}, pgd_s_per_iteration=per_iter,
+                solve_s_at_full_iterations=solve_s, wall_s=wall, pgd_evals_per_s=inc.m_cycle / per_iter,
+                p=spec.get("p"))
+    text = ("C/OpenMP restatement of DESC.m:14-263 + GCW.m (oracle/desc_full.c, desc_pgd.c; %d threads, every stage threaded) on "
+            "%s: n=%d m=%d m_cycle=%d n_sample=%d%s; stages graph %.2f s, build %.2f s, d_ijk %.2f s, GCW %.2f s; PGD timed over %d "
+            "iterations (%.3f s each, %.2e evals/s in the loop) and counted %d times: solve = %.1f s"
+            % (threads, "the workload's own graph family" + (" at full size" if spec["same_graph"] else
+                                                              " at reduced n with the same co-degree regime"),
+               inc.n, inc.m, inc.m_cycle, inc.n_sample, "" if spec.get("p") is None else " p=%.4f" % spec["p"],
+               tm["graph_s"], tm["build_s"], tm["cycle_s"], tm["gcw_s"], r["iters_run"], per_iter,
+               inc.m_cycle / per_iter, wl["iters"], solve_s))
+    return value, solve_s, info, text
 
 
 def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_sub, iters = args.cpu_n, args.cpu_iters
-    for _ in range(args.warmup and 1):
-        cpu_sample(wl, min(n_sub, 300), 2)
-    vals, times = [], []
-    info = None
-    for _ in range(max(args.steps, 1)):
-        v, dt, info = cpu_sample(wl, n_sub, iters)
+    total = max(args.steps, 1)
+    budget = max(3.0, min(args.cpu_budget, 200.0 / total))
+    if args.warmup:
+        cpu_arm(dict(wl, n=max(200, wl["n"] // 32), iters=2) if wl["kind"] == "ring" else
+                dict(wl, n=max(200, wl["n"] // 32), p=min(0.9, wl["p"] * math.sqrt(32.0)), iters=2), 5.0, k=2)
+    vals, times, info, text = [], [], None, ""
+    for _ in range(total):
+        v, solve_s, info, text = cpu_arm(wl, budget, seed=args.seed)
         vals.append(v)
-        times.append(dt)
+        times.append(solve_s)
     value = statistics.mean(vals)
-    sample = CPU_SAMPLE_TEXT % (info["n"], info["m"], info["m_cycle"], info["iters"], info["threads"],
-                                info["pgd_evals_per_s"], statistics.mean(times))
+    same = info["same_graph"]
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(times),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["name"]},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["threads"], "kind": "port", "sample": sample},
+            "config": {"workload": wl["name"] if same else
+                       "%s -- CPU arm on a reduced member of the same family: n=%d p=%s m=%d m_cycle=%d"
+                       % (wl["name"], info["n"], info["p"], info["m"], info["m_cycle"]),
+                       "same_config": same, "n": info["n"], "m": info["m"], "m_cycle": info["m_cycle"],
+                       "n_sample": info["n_sample"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["threads"], "kind": "port", "sample": text,
+                             "stage_s": info["stage_s"], "pgd_s_per_iteration": info["pgd_s_per_iteration"],
+                             "pgd_evals_per_s": info["pgd_evals_per_s"], "same_graph": same},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -153,11 +300,21 @@ def run_reference(args, wl):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+def make_model(desc_b200, wl, seed, device):
+    if wl["kind"] == "uniform":
+        return desc_b200.Uniform_Topology(wl["n"], wl["p"], wl["q"], wl["sigma"], wl["model"], seed=seed, device=device,
+                                          on_device=True)
+    if wl["kind"] == "nonuniform":
+        return desc_b200.Nonuniform_Topology(wl["n"], wl["p"], wl["p_node_crpt"], wl["p_edge_crpt"], wl["sigma"],
+                                             wl["sigma_out"], wl["crpt_type"], seed=seed, device=device, on_device=True)
+    return desc_b200.Ring_Topology(wl["n"], wl["deg"], wl["window"], wl["q"], wl["sigma"], seed=seed, device=device,
+                                   on_device=True)
+
+
 def run_gpu(args, wl):
     import numpy as np
     import torch
     import desc_b200
-    from desc_b200 import synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -171,48 +328,39 @@ def run_gpu(args, wl):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group(backend="nccl", device_id=dev)
-
-    # ---- synthetic inputs, generated on rank 0's device and broadcast so every rank holds the same graph
-    if rank == 0:
-        mo = synth.uniform_topology(wl["n"], wl["p"], wl["q"], wl["sigma"], wl["model"], seed=args.seed, device=dev)
-        m_t = torch.tensor([mo["m"]], device=dev, dtype=torch.int64)
-    else:
-        mo = None
-        m_t = torch.zeros(1, device=dev, dtype=torch.int64)
-    if world > 1:
-        dist.broadcast(m_t, 0)
-    m = int(m_t.item())
-    if rank == 0:
-        Ind_d, R_d = mo["Ind"].reshape(-1).contiguous(), mo["RijMat"].reshape(-1).contiguous()
-    else:
-        Ind_d = torch.empty(2 * m, device=dev, dtype=torch.float64)
-        R_d = torch.empty(9 * m, device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.broadcast(Ind_d, 0)
-        dist.broadcast(R_d, 0)
         idt = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
             idt = torch.frombuffer(bytearray(desc_b200.nccl_unique_id()), dtype=torch.uint8).to(dev)
         dist.broadcast(idt, 0)
         nccl_id = bytes(idt.cpu().numpy().tobytes())
-    # pinned host copies for the end-to-end arm
+
+    # ---- synthetic inputs: the library's device generator; counter-based, so every rank draws the same graph
+    mo = make_model(desc_b200, wl, args.seed, local)
+    m, n = mo.m, mo.n
+    Ind_d, R_d = mo.Ind, mo.RijMat
+    # pinned host copies for the end-to-end arm (MATLAB memory layout)
     Ind_h = torch.empty(2 * m, dtype=torch.float64).pin_memory()
     R_h = torch.empty(9 * m, dtype=torch.float64).pin_memory()
-    Ind_h.copy_(Ind_d)
-    R_h.copy_(R_d)
+    import ctypes as C
+    from desc_b200 import _lib
+    host = mo.to_host()
+    Ind_h.copy_(torch.from_numpy(host["Ind"].ravel(order="F")))
+    R_h.copy_(torch.from_numpy(host["RijMat"].ravel(order="F")))
+    truth = dict(R_orig=host["R_orig"], ErrVec=host["ErrVec"].ravel().copy(), corrupted=host["corrupted"])
+    del host
     Ind_np = Ind_h.numpy().reshape(2, m).T            # (m,2) Fortran view of the pinned buffer
     R_np = R_h.numpy().reshape(m, 3, 3).transpose(2, 1, 0)   # (3,3,m) Fortran view of the pinned buffer
     S_out = torch.empty(m, dtype=torch.float64).pin_memory()
-    R_out = torch.empty(9 * wl["n"], dtype=torch.float64).pin_memory()
+    R_out = torch.empty(9 * n, dtype=torch.float64).pin_memory()
     stream = torch.cuda.current_stream(dev)
     rule = desc_b200.ConstantStepSize(wl["lr"])
     kw = dict(device=local, stream=stream.cuda_stream, rank=rank, world=world, nccl_id=nccl_id)
     state = {}
 
     def step_resident():
-        s = desc_b200.Solver(Ind_d, R_d, n=wl["n"], **kw)
+        s = desc_b200.Solver(Ind_d, R_d, n=n, **kw)
         try:
-            info = s.build_incidence(n_sample=0, seed=1)
+            info = s.build_incidence(n_sample=wl["n_sample"], seed=1)
             s.cycle_inconsistency()
             _, _, iters_run = s.pgd(wl["iters"], rule, want_S=False, want_hist=False)
             s.gcw(want_R=False)
@@ -220,13 +368,11 @@ def run_gpu(args, wl):
         finally:
             s.close()
 
-    def step_e2e():
-        s = desc_b200.Solver(Ind_np, R_np, n=wl["n"], **kw)
+    def step_e2e(solver_kw=None):
+        s = desc_b200.Solver(Ind_np, R_np, n=n, **(solver_kw or kw))
         try:
-            s.build_incidence(n_sample=0, seed=1)
+            s.build_incidence(n_sample=wl["n_sample"], seed=1)
             s.cycle_inconsistency()
-            import ctypes as C
-            from desc_b200 import _lib
             r = rule._to_c()
             run = C.c_int32(0)
             _lib.check(s._lib.desc_b200_pgd(s._h, wl["iters"], C.byref(r), C.c_void_p(S_out.data_ptr()), None, C.byref(run)))
@@ -266,10 +412,10 @@ def run_gpu(args, wl):
 
     # the refinement stage of the full DESC() call (DESC.m:265-312), reported beside the metric (not in it)
     laa = None
-    if world == 1:
-        s = desc_b200.Solver(Ind_d, R_d, n=wl["n"], **kw)
+    if world == 1 and not args.no_side:
+        s = desc_b200.Solver(Ind_d, R_d, n=n, **kw)
         try:
-            s.build_incidence(n_sample=0, seed=1)
+            s.build_incidence(n_sample=wl["n_sample"], seed=1)
             s.cycle_inconsistency()
             s.pgd(wl["iters"], rule, want_S=False, want_hist=False)
             s.gcw(want_R=False)
@@ -283,7 +429,7 @@ def run_gpu(args, wl):
 
     # SURVEY 8(f) stages on the same graph, reported beside the metric (not in it); never fatal for the bench line
     side = None
-    if world == 1 and not args.no_side:
+    if world == 1 and not args.no_side and wl["kind"] == "uniform":
         try:
             side = side_stages(desc_b200, Ind_d, R_d, wl, kw, measured_peak()[0], args.seed)
         except Exception as e:   # noqa: BLE001
@@ -293,7 +439,44 @@ def run_gpu(args, wl):
     ms_e2e_total, _ = timed(step_e2e, max(1, min(args.steps, 3)))
     ms_e2e = ms_e2e_total / max(1, min(args.steps, 3))
     e2e = {"value": evals / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": (2 * m + 9 * m) * 8,
-           "d2h_bytes_per_step": (m + 9 * wl["n"]) * 8, "ms_per_step": ms_e2e}
+           "d2h_bytes_per_step": (m + 9 * n) * 8, "ms_per_step": ms_e2e}
+
+    # accuracy of what the timed path returned (S_out / R_out of the last e2e step) against the model's ground truth
+    quality = None
+    if rank == 0:
+        try:
+            S_np = S_out.numpy()
+            corr = truth["corrupted"]
+            Rg = np.asfortranarray(R_out.numpy().reshape(n, 3, 3).transpose(2, 1, 0))
+            _, _, mean_err, med_err = desc_b200.Rotation_Alignment(Rg, truth["R_orig"], device=local)
+            quality = {"mean_abs_S_minus_ErrVec": float(np.mean(np.abs(S_np - truth["ErrVec"]))),
+                       "mean_S_corrupted": float(S_np[corr].mean()) if corr.any() else None,
+                       "mean_S_clean": float(S_np[~corr].mean()),
+                       "gcw_rotation_error_deg_mean": float(mean_err), "gcw_rotation_error_deg_median": float(med_err)}
+        except Exception as e:   # noqa: BLE001
+            quality = {"error": "%s: %s" % (type(e).__name__, e)}
+
+    # N > 1: the N-rank result (just computed by step_e2e on every rank) against a 1-rank solve on rank 0
+    parity = None
+    if world > 1:
+        S_N = S_out.numpy().copy()
+        R_N = R_out.numpy().copy()
+        it_N = state["e2e_iters"]
+        if rank == 0:
+            step_e2e(dict(device=local, stream=stream.cuda_stream))
+            S_1, R_1 = S_out.numpy(), R_out.numpy()
+            Ra = np.asfortranarray(R_N.reshape(n, 3, 3).transpose(2, 1, 0))
+            Rb = np.asfortranarray(R_1.reshape(n, 3, 3).transpose(2, 1, 0))
+            Rab, _, _, _ = desc_b200.Rotation_Alignment(Ra, Rb, device=local)
+            D = (np.asarray(Rab) - Rb).reshape(9, n)
+            ang = np.degrees(2.0 * np.arcsin(np.minimum(np.sqrt((D ** 2).sum(axis=0)) / (2.0 * math.sqrt(2.0)), 1.0)))
+            parity = {"against": "1-rank solve of the same inputs on rank 0", "max_abs_dS_vec": float(np.max(np.abs(S_N - S_1))),
+                      "max_rel_dS_vec": float(np.max(np.abs(S_N - S_1) / np.maximum(np.abs(S_1), 1e-12))),
+                      "iters_run": [int(it_N), int(state["e2e_iters"])],
+                      "mean_rotation_angle_deg": float(ang.mean()),
+                      "ok": bool(np.max(np.abs(S_N - S_1) / np.maximum(np.abs(S_1), 1e-12)) <= 1e-10 and
+                                 it_N == state["e2e_iters"] and ang.mean() <= 1e-6)}
+        dist.barrier()
 
     per_rank = None
     if world > 1:   # per-rank kernel / collective times of the PGD iteration (load balance)
@@ -309,27 +492,35 @@ def run_gpu(args, wl):
         alg_bytes = 40.0 * local_slots + 12.0 * local_edges + 8.0 * info["m"]
         iter_ms = tm["pgd_iter_ms"]
         achieved = alg_bytes / (iter_ms * 1e-3) / 1e9 if iter_ms > 0 else 0.0
-        # DRAM bytes (read + write) of the two kernels of one iteration: `ncu --set full`, cfg 4, 1 GPU
-        # (profiles/r01_pgd_v7_*.txt); not meaningful for other workloads / shard sizes
-        traffic = NCU_TRAFFIC_CFG4 if (args.workload == "cfg4" and world == 1) else None
+        traffic, traffic_src = captured_traffic(args.workload, world)
+
+        def stage(bytes_, ms):
+            return {"algorithmic_bytes": bytes_, "ms": ms, "achieved_gbs": bytes_ / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                    "frac": bytes_ / (ms * 1e-3) / 1e9 / peak if ms > 0 else None}
+        stages = {"incidence_build": stage(24.0 * info["m"] + 20.0 * local_slots + 4.0 * local_edges, tm["build_ms"]),
+                  "d_ijk": stage(72.0 * info["m"] + 20.0 * local_slots + 4.0 * local_edges, tm["cycle_ms"])}
+        if tm.get("gcw_spmv_ms", 0) > 0:
+            stages["gcw_spmv"] = stage(88.0 * info["m"] + 144.0 * n, tm["gcw_spmv_ms"])
         roofline = {"bound": "hbm",
                     "kernel": "PGD iteration = k_pgd_stream (update, smaller endpoints) + k_pgd_passb (tables, larger endpoints)",
                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": iter_ms,
                     "kernels_ms": {"k_pgd_stream": tm.get("pgd_pass1_ms"), "k_pgd_passb": tm.get("pgd_pass2_ms")},
                     "comm_ms_per_iteration": tm.get("pgd_comm_ms"),
-                    "formula": "40*slots + 12*edges_with_cycles + 8*m (SURVEY 8d), per rank, per iteration (both kernels)"}
+                    "formula": "40*slots + 12*edges_with_cycles + 8*m (SURVEY 8d), per rank, per iteration (both kernels)",
+                    "stages": stages}
         cpu = None
         if world == 1 and not args.no_cpu:
-            v, dt, ci = cpu_sample(wl, args.cpu_n, args.cpu_iters)
-            cpu = {"value": v, "unit": UNIT, "cores": ci["threads"], "kind": "port",
-                   "sample": CPU_SAMPLE_TEXT % (ci["n"], ci["m"], ci["m_cycle"], ci["iters"], ci["threads"],
-                                                ci["pgd_evals_per_s"], dt)}
+            v, solve_s, ci, text = cpu_arm(wl, args.cpu_budget, seed=args.seed)
+            cpu = {"value": v, "unit": UNIT, "cores": ci["threads"], "kind": "port", "sample": text,
+                   "stage_s": ci["stage_s"], "pgd_s_per_iteration": ci["pgd_s_per_iteration"],
+                   "pgd_evals_per_s": ci["pgd_evals_per_s"], "same_graph": ci["same_graph"],
+                   "n": ci["n"], "m": ci["m"], "m_cycle": ci["m_cycle"]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": wl["name"], "n": wl["n"], "m": m, "m_pos": info["m_pos"],
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic (device generator csrc/gen.cu, seed %d)" % args.seed,
+                "config": {"workload": wl["name"], "n": n, "m": m, "m_pos": info["m_pos"],
                            "m_cycle": info["m_cycle"], "n_sample": info["n_sample"], "iters_run": iters_run,
                            "l2": "inputs_exceed_l2 (per-iteration working set %.1f GB)" % (alg_bytes / 1e9),
                            "parallelism": "edge-sharded x%d" % world},
@@ -337,17 +528,19 @@ def run_gpu(args, wl):
                 "pgd_evals_per_s": evals / (tm["pgd_ms"] * 1e-3) if tm["pgd_ms"] > 0 else None,
                 "stages_ms": {k: tm[k] for k in ("graph_ms", "build_ms", "cycle_ms", "pgd_ms", "gcw_ms", "pgd_iter_ms",
                                                  "pgd_pass1_ms", "pgd_pass2_ms", "pgd_comm_ms")},
+                "generator_ms": mo.gen_ms,
                 "gcw_iters": tm["gcw_iters"], "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "cpu_baseline": cpu, "clocks": clocks, "per_rank": per_rank, "laa_refine": laa,
-                "side_stages": side}
+                "cpu_baseline": cpu, "clocks": clocks, "per_rank": per_rank, "parity": parity, "quality": quality,
+                "laa_refine": laa, "side_stages": side}
         print(json.dumps(line), flush=True)
+    mo.close()
     if world > 1:
         dist.destroy_process_group()
 
 
 def side_stages(desc_b200, Ind_d, R_d, wl, kw, peak, seed):
     """CEMP / CEMP+GCW / CEMP+MST / MPLS / Spectral (the comparators Demo/compare_algorithms.m runs beside DESC) with
-    the demo's parameters on the bench graph, and the device generator of that graph; device-timed by the library."""
+    the demo's parameters on the bench graph; device-timed by the library."""
     import numpy as np
     out = {}
     s = desc_b200.Solver(Ind_d, R_d, n=wl["n"], **kw)
@@ -377,11 +570,6 @@ def side_stages(desc_b200, Ind_d, R_d, wl, kw, peak, seed):
         out["spectral_ms"] = s.timings()["gcw_ms"]
     finally:
         s.close()
-    for _ in range(2):
-        with desc_b200.Uniform_Topology(wl["n"], wl["p"], wl["q"], wl["sigma"], wl["model"], seed=seed,
-                                        device=kw["device"], on_device=True) as mo:
-            out["generator"] = {"ms": mo.gen_ms, "m": mo.m, "launches": mo.launches,
-                                "output_gbs": (168.0 * mo.m) / (mo.gen_ms * 1e-3) / 1e9}
     return out
 
 
@@ -393,8 +581,8 @@ def main():
     ap.add_argument("--impl", default="desc_b200", choices=["desc_b200", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--cpu-n", type=int, default=1500, help="nodes of the CPU-baseline sample graph")
-    ap.add_argument("--cpu-iters", type=int, default=100, help="PGD iterations of the CPU-baseline sample")
+    ap.add_argument("--cpu-budget", type=float, default=25.0,
+                    help="seconds of CPU work one CPU sample may take (sizes the sample graph)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-side", action="store_true", help="skip the SURVEY 8(f) side stages (CEMP, MPLS, ...)")
     args = ap.parse_args()
