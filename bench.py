@@ -141,8 +141,8 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU arm: the C/OpenMP restatement on the workload's own graph family
 # ------------------------------------------------------------------------------------------
-# thread-seconds per slot measured on the build container (8 Xeon threads, cfg-4 graph): used only to size the sample
-CPU_COST_FIXED, CPU_COST_ITER = 9.4e-7, 1.2e-7
+# thread-seconds per slot (between the build container and the GPU boxes' hosts): used only to size the sample
+CPU_COST_FIXED, CPU_COST_ITER = 6.0e-7, 7.0e-8
 _CPU_INPUTS = {}
 
 
