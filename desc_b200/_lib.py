@@ -70,7 +70,7 @@ class Timings(C.Structure):
                 ("reserved", C.c_int32), ("pgd_pass1_ms", C.c_double), ("pgd_pass2_ms", C.c_double),
                 ("pgd_comm_ms", C.c_double), ("laa_ms", C.c_double), ("laa_iters", C.c_int32), ("laa_cg_iters", C.c_int32),
                 ("cemp_ms", C.c_double), ("cemp_iters", C.c_int32), ("reserved2", C.c_int32),
-                ("mst_ms", C.c_double)]
+                ("mst_ms", C.c_double), ("gcw_spmv_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}

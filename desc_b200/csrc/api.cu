@@ -74,12 +74,14 @@ void desc_b200_destroy(desc_b200_handle* h) {
                     h->gcw_small, h->gcw_res, h->R_est, h->d_err, h->d_Sin, h->rk_i, h->rk_j, h->estart,
                     h->pgd_partial, h->jhdr, h->sjk, h->thr_key, h->thr_k, h->comm_scratch,
                     h->cemp_S[0], h->cemp_S[1], h->diag_work, h->diag_hist, h->R_mst, h->ell_vtile, h->ell_tiles,
-                    h->ell_tcnt, h->ell_d, h->ell_rk, h->ell_pj, h->ell_w[0], h->ell_w[1], h->ell_adam_m, h->ell_adam_v};
+                    h->ell_tcnt, h->ell_d, h->ell_rk, h->ell_pj, h->ell_w[0], h->ell_w[1], h->ell_adam_m, h->ell_adam_v,
+                    h->gcw_coef_adj};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_ctrl) cudaFreeHost(h->h_ctrl);
     if (h->gcw_res_host) cudaFreeHost(h->gcw_res_host);
     for (cudaEvent_t e : h->iter_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->spmv_events) cudaEventDestroy(e);
     cudaEvent_t evs[] = {h->ev0, h->ev1, h->ev2, h->ev3};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);

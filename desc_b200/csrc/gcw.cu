@@ -75,6 +75,12 @@ __global__ void k_gcw_coef(const int* __restrict__ ei, const int* __restrict__ e
     int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e < m) coef[e] = omega[e] * isd[ei[e]] * isd[ej[e]];
 }
+// the same coefficients in adjacency order (what the SpMV streams)
+__global__ void k_gcw_coef_adj(const int* __restrict__ adj_eid, const double* __restrict__ coef, int64_t n2m,
+                               double* __restrict__ coef_adj) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p < n2m) coef_adj[p] = coef[adj_eid[p]];
+}
 
 __global__ void k_gcw_init(double* __restrict__ X, int64_t n9) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -83,31 +89,61 @@ __global__ void k_gcw_init(double* __restrict__ X, int64_t n9) {
     X[t] = (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
 }
 
-// Y[node] = sum_p coef * op(R_e) * X[nbr] for node in [n0, n1)
-__global__ void __launch_bounds__(256)
+// Y[node] = sum_p coef * op(R_e) * X[nbr] for node in [n0, n1).
+// One warp per node, 32 adjacency entries at a time.  The two 72-byte records of an entry (R_e and the neighbour's X
+// block; 8-byte aligned, so no vector loads) are gathered COOPERATIVELY like in cycle.cu: in 9 rounds lane L loads word
+// 32 t + L of the 32 concatenated records -- 9 consecutive lanes read one record as one contiguous piece (1-2 L1
+// wavefronts per record instead of 9) -- and a per-warp staging buffer (stride 9 doubles, conflict-free) hands the
+// record to the lane that owns the entry.  coef is kept in adjacency order (coalesced).
+#define SPMV_WARPS 8
+__global__ void __launch_bounds__(SPMV_WARPS * 32)
 k_gcw_spmv(const int* __restrict__ rowstart, const int* __restrict__ adj_nbr,
            const int* __restrict__ adj_eid, const double* __restrict__ Rij,
-           const double* __restrict__ coef, const double* __restrict__ X, double* __restrict__ Y,
+           const double* __restrict__ coef_adj, const double* __restrict__ X, double* __restrict__ Y,
            int n0, int n1) {
-    const int node = n0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    __shared__ double stage[SPMV_WARPS][2][288];
+    const int wib = threadIdx.x >> 5;
+    const int node = n0 + blockIdx.x * SPMV_WARPS + wib;
     const int lane = threadIdx.x & 31;
     if (node >= n1) return;
+    double* sr = stage[wib][0];
+    double* sx = stage[wib][1];
     double acc[9];
 #pragma unroll
     for (int x = 0; x < 9; x++) acc[x] = 0.0;
-    const int p1 = rowstart[node + 1];
-    for (int p = rowstart[node] + lane; p < p1; p += 32) {
-        const int nb = adj_nbr[p];
-        const int e = adj_eid[p];
-        const double c = coef[e];
-        const double* pr = Rij + 9 * (int64_t)e;
-        const double* px = X + 9 * (int64_t)nb;
+    const int p0 = rowstart[node], p1 = rowstart[node + 1];
+    for (int pb = p0; pb < p1; pb += 32) {
+        const int p = pb + lane;
+        const bool ok = p < p1;
+        int nb = 0, e = 0;
+        double c = 0.0;
+        if (ok) {
+            nb = adj_nbr[p];
+            e = adj_eid[p];
+            c = coef_adj[p];
+        }
+        const int cnt = min(32, p1 - pb);
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            const int w = t * 32 + lane;
+            const int rec = w / 9, el = w - 9 * rec;
+            const int qe = __shfl_sync(0xffffffffu, e, rec), qn = __shfl_sync(0xffffffffu, nb, rec);
+            double vr = 0.0, vx = 0.0;
+            if (rec < cnt) {
+                vr = __ldg(Rij + 9 * (int64_t)qe + el);
+                vx = X[9 * (int64_t)qn + el];
+            }
+            sr[w] = vr;
+            sx[w] = vx;
+        }
+        __syncwarp();
         double r[9], x[9];
 #pragma unroll
         for (int q = 0; q < 9; q++) {
-            r[q] = __ldg(pr + q);
-            x[q] = px[q];
+            r[q] = sr[9 * lane + q];
+            x[q] = sx[9 * lane + q];
         }
+        __syncwarp();
         if (node < nb) {
             // block (node, nb) = c * R_e : y(a,col) += c * sum_b R(a,b) x(b,col)
 #pragma unroll
@@ -185,12 +221,25 @@ k_gcw_reduce(const double* __restrict__ X, const double* __restrict__ Y, int n,
 // one thread: H, G from partials; Cholesky of G = L L'; T = inv(L)' (so Q = Y T), R = L' (Y = Q R).
 // accumulate != 0: R <- R_new * R_old (second Cholesky-QR pass).  A pivot that collapses relative
 // to the block's scale raises the breakdown flag (the block is numerically rank deficient).
+// (launched with one warp: lane l sums the partials of blocks l, l+32, ... and a fixed-shape shuffle tree adds the
+// lanes -- deterministic, and ~20x shorter than the serial sum of 148 x 15 dependent loads it replaces)
+template <int K>
+__device__ __forceinline__ void warp_sum_partials(const double* __restrict__ partial, int nblocks, int offset, double (&s)[K]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int x = 0; x < K; x++) s[x] = 0.0;
+    for (int b = lane; b < nblocks; b += 32)
+#pragma unroll
+        for (int x = 0; x < K; x++) s[x] += partial[(size_t)b * GCW_NRED + offset + x];
+#pragma unroll
+    for (int x = 0; x < K; x++) s[x] = group_sum<32>(s[x]);
+}
+
 __global__ void k_gcw_small_orth(const double* __restrict__ partial, int nblocks,
                                  double* __restrict__ small, int accumulate) {
     double s[15];
-    for (int x = 0; x < 15; x++) s[x] = 0.0;
-    for (int b = 0; b < nblocks; b++)
-        for (int x = 0; x < 15; x++) s[x] += partial[(size_t)b * GCW_NRED + x];
+    warp_sum_partials<15>(partial, nblocks, 0, s);
+    if (threadIdx.x != 0) return;
     for (int x = 0; x < 9; x++) small[SM_H + x] = s[x];
     const double g00 = s[9], g01 = s[10], g02 = s[11], g11 = s[12], g12 = s[13], g22 = s[14];
     const double scale = fmax(g00, fmax(g11, g22));
@@ -289,8 +338,10 @@ k_gcw_residual(const double* __restrict__ X, const double* __restrict__ Y, int n
 
 __global__ void k_gcw_small_res(const double* __restrict__ partial, int nblocks,
                                 double* __restrict__ small, double* __restrict__ res_hist, int it) {
-    double s = 0.0;
-    for (int b = 0; b < nblocks; b++) s += partial[(size_t)b * GCW_NRED + 15];
+    double sv[1];
+    warp_sum_partials<1>(partial, nblocks, 15, sv);
+    if (threadIdx.x != 0) return;
+    const double s = sv[0];
     small[SM_RES] = s;
     res_hist[it] = sqrt(s);
 }
@@ -372,9 +423,9 @@ k_gcw_ritz_apply(const double* __restrict__ X, const double* __restrict__ isd, i
 // column norms + sign rule of GCW.m:28 (det of the first node's block after normalisation)
 __global__ void k_gcw_small_final(const double* __restrict__ partial, int nblocks,
                                   const double* __restrict__ V, double* __restrict__ small) {
-    double s[3] = {0.0, 0.0, 0.0};
-    for (int b = 0; b < nblocks; b++)
-        for (int x = 0; x < 3; x++) s[x] += partial[(size_t)b * GCW_NRED + x];
+    double s[3];
+    warp_sum_partials<3>(partial, nblocks, 0, s);
+    if (threadIdx.x != 0) return;
     double sc[3];
     for (int x = 0; x < 3; x++) {
         sc[x] = 1.0 / sqrt(s[x]);
@@ -600,15 +651,24 @@ struct Lanczos {
     double* hist_r;  // per step: 16
     double* Zdev;    // rotation coefficients
     double* host;    // pinned staging
+    int spmv_count = 0;
 
     double* blk(int b) const { return V + (size_t)b * n9; }
 
     int spmv(const double* X, double* Y) {
-        const unsigned grid = (unsigned)((((int64_t)(n1 - n0)) * 32 + 255) / 256);
+        const unsigned grid = (unsigned)((n1 - n0 + SPMV_WARPS - 1) / SPMV_WARPS);
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (spmv_count < (int)h->spmv_events.size() / 2) {
+            e0 = h->spmv_events[2 * spmv_count];
+            e1 = h->spmv_events[2 * spmv_count + 1];
+        }
+        if (e0) CUDA_TRY(cudaEventRecord(e0, h->stream));
         if (grid > 0) {
-            k_gcw_spmv<<<grid, 256, 0, h->stream>>>(h->rowstart, h->adj_nbr, h->adj_eid, h->Rij, h->gcw_coef, X, Y, n0, n1);
+            k_gcw_spmv<<<grid, SPMV_WARPS * 32, 0, h->stream>>>(h->rowstart, h->adj_nbr, h->adj_eid, h->Rij, h->gcw_coef_adj, X, Y, n0, n1);
             KERNEL_CHECK(h);
         }
+        if (e1) CUDA_TRY(cudaEventRecord(e1, h->stream));
+        spmv_count++;
         DESC_TRY(desc_allgather_ranges(h, Y, sizeof(double), nb9));
         return DESC_B200_OK;
     }
@@ -631,7 +691,7 @@ struct Lanczos {
         for (int pass = 0; pass < 2; pass++) {
             k_gcw_reduce<<<GCW_RED_BLOCKS, GCW_RED_TB, 0, h->stream>>>(blk(w), blk(w), n, h->gcw_red);
             KERNEL_CHECK(h);
-            k_gcw_small_orth<<<1, 1, 0, h->stream>>>(h->gcw_red, GCW_RED_BLOCKS, h->gcw_small, pass);
+            k_gcw_small_orth<<<1, 32, 0, h->stream>>>(h->gcw_red, GCW_RED_BLOCKS, h->gcw_small, pass);
             KERNEL_CHECK(h);
             k_gcw_apply<<<GCW_RED_BLOCKS, GCW_RED_TB, 0, h->stream>>>(blk(w), blk(w), n, h->gcw_small, h->gcw_red);
             KERNEL_CHECK(h);
@@ -665,6 +725,7 @@ int desc_gcw_impl(desc_b200_handle* h, const double* d_S) {
     if (!h->omega) {
         CUDA_TRY(cudaMalloc(&h->omega, m * sizeof(double)));
         CUDA_TRY(cudaMalloc(&h->gcw_coef, m * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->gcw_coef_adj, 2 * m * sizeof(double)));
         CUDA_TRY(cudaMalloc(&h->isd, (size_t)n * sizeof(double)));
         CUDA_TRY(cudaMalloc(&h->X[0], (size_t)total_blocks * n9 * sizeof(double)));
         CUDA_TRY(cudaMalloc(&h->X[1], n9 * sizeof(double)));
@@ -719,6 +780,13 @@ int desc_gcw_impl(desc_b200_handle* h, const double* d_S) {
     KERNEL_CHECK(h);
     k_gcw_coef<<<gbm, 256, 0, st>>>(h->ei, h->ej, h->omega, h->isd, m, h->gcw_coef);
     KERNEL_CHECK(h);
+    k_gcw_coef_adj<<<(unsigned)((2 * m + 255) / 256), 256, 0, st>>>(h->adj_eid, h->gcw_coef, 2 * m, h->gcw_coef_adj);
+    KERNEL_CHECK(h);
+    while (h->spmv_events.size() < 2 * 32) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        h->spmv_events.push_back(e);
+    }
 
     // projected matrix on the host: Hm is (3*cap) x (3*cap), column-major
     const int cap = GCW_DMAX + 2;
@@ -836,11 +904,11 @@ int desc_gcw_impl(desc_b200_handle* h, const double* d_S) {
             total_spmv++;
             k_gcw_reduce<<<GCW_RED_BLOCKS, GCW_RED_TB, 0, st>>>(X, Y, n, h->gcw_red);
             KERNEL_CHECK(h);
-            k_gcw_small_orth<<<1, 1, 0, st>>>(h->gcw_red, GCW_RED_BLOCKS, h->gcw_small, 0);
+            k_gcw_small_orth<<<1, 32, 0, st>>>(h->gcw_red, GCW_RED_BLOCKS, h->gcw_small, 0);
             KERNEL_CHECK(h);
             k_gcw_residual<<<GCW_RED_BLOCKS, GCW_RED_TB, 0, st>>>(X, Y, n, h->gcw_small, h->gcw_red);
             KERNEL_CHECK(h);
-            k_gcw_small_res<<<1, 1, 0, st>>>(h->gcw_red, GCW_RED_BLOCKS, h->gcw_small, L.c, 0);
+            k_gcw_small_res<<<1, 32, 0, st>>>(h->gcw_red, GCW_RED_BLOCKS, h->gcw_small, L.c, 0);
             KERNEL_CHECK(h);
             CUDA_TRY(cudaMemcpyAsync(L.host, L.c, sizeof(double), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
@@ -891,10 +959,22 @@ int desc_gcw_impl(desc_b200_handle* h, const double* d_S) {
     double* Vout = L.blk(0);
     k_gcw_ritz_apply<<<GCW_RED_BLOCKS, GCW_RED_TB, 0, st>>>(X, h->isd, n, h->gcw_small, Vout, h->gcw_red);
     KERNEL_CHECK(h);
-    k_gcw_small_final<<<1, 1, 0, st>>>(h->gcw_red, GCW_RED_BLOCKS, Vout, h->gcw_small);
+    k_gcw_small_final<<<1, 32, 0, st>>>(h->gcw_red, GCW_RED_BLOCKS, Vout, h->gcw_small);
     KERNEL_CHECK(h);
     k_gcw_project<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(Vout, h->gcw_small, n, h->R_est);
     KERNEL_CHECK(h);
     CUDA_TRY(cudaStreamSynchronize(st));
+    {   // mean device time of one SpMV kernel (bench: roofline of the block-sparse product)
+        double tot = 0.0;
+        int cnt = 0;
+        for (int k = 0; k < std::min(L.spmv_count, (int)h->spmv_events.size() / 2); k++) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, h->spmv_events[2 * k], h->spmv_events[2 * k + 1]) == cudaSuccess) {
+                tot += ms;
+                cnt++;
+            }
+        }
+        h->tm.gcw_spmv_ms = cnt > 0 ? tot / cnt : 0.0;
+    }
     return DESC_B200_OK;
 }

@@ -155,6 +155,8 @@ struct desc_b200_handle {
     double* isd = nullptr;      // n: 1/sqrt(d_i)
     double* X[2] = {nullptr, nullptr};  // 9n each
     double* gcw_coef = nullptr; // m: omega_e / sqrt(d_i d_j)
+    double* gcw_coef_adj = nullptr;  // 2m: the same in adjacency order (streamed by the SpMV)
+    std::vector<cudaEvent_t> spmv_events;
     double* gcw_red = nullptr;  // reduction scratch
     double* gcw_small = nullptr;  // 3x3 transforms etc.
     double* gcw_res = nullptr;  // residual history (device)

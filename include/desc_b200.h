@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define DESC_B200_VERSION 101
+#define DESC_B200_VERSION 102
 
 #define DESC_B200_OK 0
 #define DESC_B200_ERR_ARG -1      /* bad argument / input violates the layout contract */
@@ -104,6 +104,7 @@ typedef struct desc_b200_timings {
     int32_t cemp_iters;   /* reweighting iterations of the last cemp call                     */
     int32_t reserved2;
     double mst_ms;        /* mst_init: spanning tree + propagation                            */
+    double gcw_spmv_ms;   /* gcw: mean device time of one block-sparse SpMV kernel            */
 } desc_b200_timings;
 
 const char* desc_b200_last_error(void);

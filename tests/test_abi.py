@@ -25,7 +25,7 @@ def test_library_exports_every_header_symbol():
     lib = _lib.load()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.desc_b200_version() == 101
+    assert lib.desc_b200_version() == 102
 
 
 def test_struct_layouts_match_header(tmp_path):
