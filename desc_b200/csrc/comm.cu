@@ -29,6 +29,7 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -61,6 +62,7 @@ int nccl_load() {
     LOAD(AllReduce, "ncclAllReduce");
     LOAD(Broadcast, "ncclBroadcast");
     LOAD(AllGather, "ncclAllGather");
+    LOAD(ReduceScatter, "ncclReduceScatter");
     LOAD(Send, "ncclSend");
     LOAD(Recv, "ncclRecv");
     LOAD(GroupStart, "ncclGroupStart");
@@ -143,12 +145,83 @@ int desc_allreduce_sum(desc_b200_handle* h, double* buf, int64_t count) {
     return DESC_B200_OK;
 }
 
+// ---- the two per-iteration exchanges as NCCL collectives on padded, rank-major staging -------------------------
+// The shards are ragged (vertex-aligned edge ranges), NCCL's all-gather / reduce-scatter want equal counts: pack the
+// ranges into slots of the largest range's size, run ONE collective (NVSwitch: ring / NVLS inside NCCL, all links
+// busy), unpack.  Measured against the grouped point-to-point version below (which NCCL serves with few channels
+// per peer): profiles/README.md, round 2.  DESC_B200_COMM=p2p selects the point-to-point version.
+static bool use_collectives(size_t staging_bytes) {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("DESC_B200_COMM");
+        mode = (e && strcmp(e, "p2p") == 0) ? 0 : 1;
+    }
+    return mode == 1 && staging_bytes <= ((size_t)1 << 30);
+}
+static int comm_scratch_need(desc_b200_handle* h, size_t need) {
+    if (h->comm_scratch_bytes < need) {
+        if (h->comm_scratch) cudaFree(h->comm_scratch);
+        h->comm_scratch = nullptr;
+        h->comm_scratch_bytes = 0;
+        CUDA_TRY(cudaMalloc(&h->comm_scratch, need));
+        h->comm_scratch_bytes = need;
+    }
+    return DESC_B200_OK;
+}
+struct RangeTab {
+    int64_t b[65];
+    int world;
+};
+// words of 4 bytes: dst slot r (stride words) <- src range r, or back (pack = 1: ranges -> slots)
+__global__ void k_pack_ranges(uint32_t* __restrict__ slots, uint32_t* __restrict__ flat, RangeTab t, int64_t stride,
+                              int words_per_elem, int pack, int only, int skip) {
+    const int r = blockIdx.y;
+    if ((only >= 0 && r != only) || r == skip) return;
+    const int64_t n = (t.b[r + 1] - t.b[r]) * words_per_elem;
+    uint32_t* f = flat + t.b[r] * words_per_elem;
+    uint32_t* s = slots + r * stride;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (pack)
+            s[i] = f[i];
+        else
+            f[i] = s[i];
+    }
+}
+
+static int allgather_collective(desc_b200_handle* h, void* buf, size_t elem_bytes, const std::vector<int64_t>& bounds) {
+    const int W = h->world, me = h->rank;
+    int64_t maxr = 0;
+    for (int r = 0; r < W; r++) maxr = std::max<int64_t>(maxr, bounds[r + 1] - bounds[r]);
+    if (maxr == 0) return DESC_B200_OK;
+    const int wpe = (int)(elem_bytes / 4);
+    const int64_t stride = maxr * wpe;                           // words per slot
+    DESC_TRY(comm_scratch_need(h, (size_t)W * stride * 4));
+    uint32_t* st = (uint32_t*)h->comm_scratch;
+    RangeTab t;
+    t.world = W;
+    for (int r = 0; r <= W; r++) t.b[r] = bounds[r];
+    dim3 g(DESC_SMS * 2, W);
+    k_pack_ranges<<<g, 256, 0, h->stream>>>(st, (uint32_t*)buf, t, stride, wpe, 1, me, -1);
+    KERNEL_CHECK(h);
+    NCCL_TRY(g_nccl.AllGather(st + (int64_t)me * stride, st, (size_t)stride, ncclUint32, (ncclComm_t)h->comm, h->stream));
+    k_pack_ranges<<<g, 256, 0, h->stream>>>(st, (uint32_t*)buf, t, stride, wpe, 0, -1, me);
+    KERNEL_CHECK(h);
+    h->collectives++;
+    return DESC_B200_OK;
+}
+
 // in-place ragged all-gather: rank r owns elements [bounds[r], bounds[r+1]) of buf.  Point-to-point
 // sends/receives in one group (all pairs move concurrently over NVSwitch) instead of `world`
 // broadcasts, which NCCL runs one after the other.
 int desc_allgather_ranges(desc_b200_handle* h, void* buf, size_t elem_bytes,
                           const std::vector<int64_t>& bounds) {
     if (h->world <= 1) return DESC_B200_OK;
+    {
+        int64_t maxr = 0;
+        for (int r = 0; r < h->world; r++) maxr = std::max<int64_t>(maxr, bounds[r + 1] - bounds[r]);
+        if (elem_bytes % 4 == 0 && h->world <= 64 && use_collectives((size_t)h->world * maxr * elem_bytes))
+            return allgather_collective(h, buf, elem_bytes, bounds);
+    }
     const int me = h->rank;
     char* mine = (char*)buf + (size_t)bounds[me] * elem_bytes;
     const size_t my_bytes = (size_t)(bounds[me + 1] - bounds[me]) * elem_bytes;
@@ -194,10 +267,55 @@ __global__ void k_sum_partials_u64(unsigned long long* __restrict__ own, const u
     own[i] = acc;
 }
 
+// slots for the reduce-scatter: slot r = [range r of buf (width doubles per element), zero padding, the `tail` doubles]
+// -- every rank puts its tail partial into EVERY slot, so each rank receives the tail's sum with its own range
+__global__ void k_pack_reduce(double* __restrict__ slots, const double* __restrict__ buf, RangeTab t, int64_t stride,
+                              int width, int tail) {
+    const int r = blockIdx.y;
+    const int64_t n = (t.b[r + 1] - t.b[r]) * width;
+    const double* f = buf + t.b[r] * width;
+    double* s = slots + r * stride;
+    const int64_t body = stride - tail;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < stride; i += (int64_t)gridDim.x * blockDim.x)
+        s[i] = i < n ? f[i] : (i >= body ? buf[t.b[t.world] * width + (i - body)] : 0.0);
+}
+__global__ void k_unpack_reduce(const double* __restrict__ recv, double* __restrict__ buf, int64_t begin, int64_t n,
+                                int64_t body, int64_t tail_at, int tail) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n + tail; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < n)
+            buf[begin + i] = recv[i];
+        else
+            buf[tail_at + (i - n)] = recv[body + (i - n)];
+    }
+}
+
 int desc_reduce_to_owners(desc_b200_handle* h, double* buf, int width, const std::vector<int64_t>& bounds,
                           int tail, bool body_u64) {
     if (h->world <= 1) return DESC_B200_OK;
     const int me = h->rank, W = h->world;
+    if (!body_u64 && W <= 64) {
+        int64_t mx = 0;
+        for (int r = 0; r < W; r++) mx = std::max<int64_t>(mx, bounds[r + 1] - bounds[r]);
+        const int64_t stride = mx * width + tail;
+        if (use_collectives((size_t)(W + 1) * stride * sizeof(double))) {
+            DESC_TRY(comm_scratch_need(h, (size_t)(W + 1) * stride * sizeof(double)));
+            double* send = (double*)h->comm_scratch;
+            double* recv = send + (int64_t)W * stride;
+            RangeTab t;
+            t.world = W;
+            for (int r = 0; r <= W; r++) t.b[r] = bounds[r];
+            dim3 g(DESC_SMS * 2, W);
+            k_pack_reduce<<<g, 256, 0, h->stream>>>(send, buf, t, stride, width, tail);
+            KERNEL_CHECK(h);
+            NCCL_TRY(g_nccl.ReduceScatter(send, recv, (size_t)stride, ncclFloat64, ncclSum, (ncclComm_t)h->comm, h->stream));
+            const int64_t n = (bounds[me + 1] - bounds[me]) * width;
+            k_unpack_reduce<<<DESC_SMS * 2, 256, 0, h->stream>>>(recv, buf, bounds[me] * width, n, stride - tail,
+                                                                bounds[W] * width, tail);
+            KERNEL_CHECK(h);
+            h->collectives++;
+            return DESC_B200_OK;
+        }
+    }
     const int64_t total = bounds[W];
     int64_t maxr = 0;
     for (int r = 0; r < W; r++) maxr = std::max<int64_t>(maxr, bounds[r + 1] - bounds[r]);

@@ -6,7 +6,8 @@
 Every rank solves the same graph (a) alone (world=1) and (b) as its shard of the N-rank solve, and
 checks: identical iters_run, S_vec within 1e-12, objective history within 1e-11,
 rotations within 1e-6 deg; CEMP's SVec bit-identical (per-edge arithmetic does not depend on the shard) and
-CEMP+GCW rotations within 1e-6 deg.  Prints MULTI_GPU_OK on rank 0 when all ranks agree.
+CEMP+GCW rotations within 1e-6 deg.  With ``--full`` the same comparison also runs at cfg-4 size (n=10000, p=0.1,
+1.5e8 slots, inputs from the device generator).  Prints MULTI_GPU_OK on rank 0 when all ranks agree.
 """
 import os
 import sys
@@ -77,6 +78,25 @@ def main():
             rank, case, one["k"], many["k"], dS, dh, ang, dC, angC, angL, angM, a["edge_begin"], a["edge_end"], a["local_slots"],
             "ok" if good else "MISMATCH"), flush=True)
         ok = ok and good
+    if "--full" in sys.argv:
+        # cfg-4 size (n=10000, p=0.1: 5.0e6 edges, 1.5e8 slots) through the same comparison: N-rank == 1-rank
+        with desc_b200.Uniform_Topology(10000, 0.1, 0.2, 0.1, "uniform", seed=0, device=local, on_device=True) as mo:
+            nccl_id = ddist.exchange_nccl_id(desc_b200.nccl_unique_id, device="cuda")
+            res = []
+            for (rk, wd, nid) in ((0, 1, None), (rank, world, nccl_id)):
+                with desc_b200.Solver(mo.Ind, mo.RijMat, n=mo.n, device=local, rank=rk, world=wd, nccl_id=nid) as s:
+                    info = s.build_incidence(n_sample=0, seed=1)
+                    s.cycle_inconsistency()
+                    S, hist, k = s.pgd(12, desc_b200.ConstantStepSize(0.01))
+                    res.append(dict(info=info, S=S, hist=hist, k=k, R=s.gcw()))
+            one, many = res
+            dS = float(np.max(np.abs(one["S"] - many["S"]) / np.maximum(np.abs(one["S"]), 1e-12)))
+            dh = float(np.max(np.abs(one["hist"][:, 1] - many["hist"][:, 1]) / np.maximum(np.abs(one["hist"][:, 1]), 1e-9)))
+            ang = float(O.aligned_angle_deg(one["R"], many["R"]).mean())
+            good = one["k"] == many["k"] and dS <= 1e-10 and dh <= 1e-11 and ang <= 1e-6
+            print("rank %d cfg4: iters %d/%d rel dS=%.2e dobj=%.2e dR=%.2e deg slots=%d %s" % (
+                rank, one["k"], many["k"], dS, dh, ang, many["info"]["local_slots"], "ok" if good else "MISMATCH"), flush=True)
+            ok = ok and good
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:

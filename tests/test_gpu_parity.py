@@ -347,7 +347,8 @@ def test_multi_gpu_parity_when_more_than_one_device():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
                         "--master-addr", "127.0.0.1", "--master-port", "29517",
-                        os.path.join(root, "tests", "multi_gpu_check.py")], capture_output=True, text=True, timeout=900)
+                        os.path.join(root, "tests", "multi_gpu_check.py"), "--full"], capture_output=True, text=True,
+                       timeout=1200)
     assert "MULTI_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
