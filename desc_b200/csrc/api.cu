@@ -67,6 +67,7 @@ void desc_b200_destroy(desc_b200_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     desc_comm_destroy(h);
+    if (h->S_in_sym) h->S[0] = h->S[1] = nullptr;   // they live in the communicator's peer-mapped region
     void* ptrs[] = {h->ei, h->ej, h->Rij_owned, h->bm, h->bmprefix, h->rowstart, h->adj_nbr, h->adj_eid,
                     h->codeg, h->rowptr, h->apex, h->pk_jk, h->pk_ki, h->S0, h->w[0], h->w[1],
                     h->S[0], h->S[1], h->acc[0], h->acc[1], h->adam_m, h->adam_v, h->d_hist, h->d_ctrl,
@@ -272,16 +273,18 @@ int desc_b200_refine(desc_b200_handle* h, const double* S_vec, const double* R_i
         }
         d_S = h->S[h->final_buf];
     }
+    DescTmp t_R, t_out;   // returned to the pool on every exit path
     double* d_R = nullptr;
     if (R_init) {
-        CUDA_TRY(cudaMalloc(&d_R, 9 * (size_t)h->n * sizeof(double)));
+        CUDA_TRY(t_R.alloc(9 * (size_t)h->n * sizeof(double)));
+        d_R = t_R.as<double>();
         CUDA_TRY(cudaMemcpyAsync(d_R, R_init, 9 * (size_t)h->n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     } else if (!h->have_gcw) {
         desc_set_error("refine with R_init=NULL needs a previous gcw on this handle");
         return DESC_B200_ERR_STATE;
     }
-    double* d_out = nullptr;
-    CUDA_TRY(cudaMalloc(&d_out, 9 * (size_t)h->n * sizeof(double)));
+    CUDA_TRY(t_out.alloc(9 * (size_t)h->n * sizeof(double)));
+    double* d_out = t_out.as<double>();
     int run = 0, rc;
     {
         StageTimer t(h, &h->tm.laa_ms);
@@ -296,8 +299,6 @@ int desc_b200_refine(desc_b200_handle* h, const double* S_vec, const double* R_i
             rc = DESC_B200_ERR_CUDA;
         }
     }
-    cudaFree(d_out);
-    if (d_R) cudaFree(d_R);
     if (iters_run) *iters_run = run;
     h->tm.laa_iters = run;
     h->tm.laa_cg_iters = h->laa_cg_iters;

@@ -524,6 +524,170 @@ __global__ void k_fill_slots(FillArgs a) {
     }
 }
 
+// Register-resident version of k_fill_slots for co-degrees up to 32 T (cfg 4: T = 8, cfg 2: T = 16): candidate
+// q = lane + 32 t lives in register t of its lane.  The MSB-first radix selection then costs one ballot + popc per
+// register and bit (no shared-memory state, no second pass to update it), and the bitmap rows are ANDed with 128-bit
+// loads.  Same selection rule and the same outputs as k_fill_slots (bit-exact; tests compare both with the oracle).
+template <int T>
+__global__ void __launch_bounds__(256)
+k_fill_slots_reg(FillArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    int* ck = reinterpret_cast<int*>(smem_raw) + (size_t)wib * (32 * T);
+    const unsigned lt = (1u << lane) - 1u;
+    const int nq = a.nwords >> 2;
+    const int64_t warp = (int64_t)blockIdx.x * wpb + wib;
+    const int64_t nwarps = (int64_t)gridDim.x * wpb;
+    for (int64_t e = a.e0 + warp; e < a.e1; e += nwarps) {
+        const int c = a.codeg[e];
+        if (c == 0) continue;
+        const int i = a.ei[e], j = a.ej[e];
+        const uint4* ri = reinterpret_cast<const uint4*>(a.bm + (size_t)i * a.nwords);
+        const uint4* rj = reinterpret_cast<const uint4*>(a.bm + (size_t)j * a.nwords);
+        // common neighbours in ascending order -> ck[0..c)
+        int run = 0;
+        for (int qb = 0; qb < nq; qb += 32) {
+            const int q = qb + lane;
+            uint4 x = make_uint4(0u, 0u, 0u, 0u);
+            if (q < nq) {
+                const uint4 u = ri[q], v = rj[q];
+                x = make_uint4(u.x & v.x, u.y & v.y, u.z & v.z, u.w & v.w);
+            }
+            const int cnt = __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            int pos = run + inc - cnt;
+            const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int wi = 0; wi < 4; wi++) {
+                uint32_t y = xs[wi];
+                while (y) {
+                    const int b = __ffs(y) - 1;
+                    y &= y - 1;
+                    ck[pos++] = ((4 * q + wi) << 5) + b;
+                }
+            }
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        __syncwarp();
+        int kk[T];
+#pragma unroll
+        for (int t = 0; t < T; t++) kk[t] = lane + 32 * t < c ? ck[lane + 32 * t] : -1;
+        __syncwarp();
+        const bool sample = c > a.n_sample;   // len==n_sample keeps everything (DESC.m:83)
+        uint32_t sel = 0u;                    // bit t: candidate of register t is in the slot list
+#pragma unroll
+        for (int t = 0; t < T; t++) sel |= (kk[t] >= 0 ? 1u : 0u) << t;
+        uint64_t tkey = ~0ull;
+        int tk = 0x7fffffff;
+        if (sample) {
+            uint64_t key[T];
+#pragma unroll
+            for (int t = 0; t < T; t++) key[t] = kk[t] >= 0 ? desc_key(a.seed, (uint64_t)e, (uint64_t)kk[t]) : ~0ull;
+            uint32_t und = sel;
+            sel = 0u;
+            int need = a.n_sample, undc = c;
+            for (int bit = 63; bit >= 0 && need > 0 && undc > need; bit--) {
+                uint32_t zero = 0u;
+                int cnt0 = 0;
+#pragma unroll
+                for (int t = 0; t < T; t++) {
+                    const bool p = ((und >> t) & 1u) && !((key[t] >> bit) & 1ull);
+                    cnt0 += __popc(__ballot_sync(0xffffffffu, p));
+                    zero |= (p ? 1u : 0u) << t;
+                }
+                if (cnt0 <= need) {   // all undecided keys with a 0 bit are among the smallest
+                    sel |= zero;
+                    und &= ~zero;
+                    need -= cnt0;
+                    undc -= cnt0;
+                } else {              // the n_sample-th smallest has a 0 bit: keys with a 1 bit are out
+                    und = zero;
+                    undc = cnt0;
+                }
+            }
+            // the rest: exactly `need` undecided keys left, or equal keys (smallest apices first: candidates are in
+            // ascending apex order, q = lane + 32 t)
+            int taken = 0;
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+                const bool u = (und >> t) & 1u;
+                const unsigned bal = __ballot_sync(0xffffffffu, u);
+                if (u && taken + __popc(bal & lt) < need) sel |= 1u << t;
+                taken += __popc(bal);
+            }
+            // threshold = largest selected (key, apex)
+            uint64_t mk = 0ull;
+            int mv = -1;
+#pragma unroll
+            for (int t = 0; t < T; t++)
+                if (((sel >> t) & 1u) && (key[t] > mk || (key[t] == mk && kk[t] > mv))) {
+                    mk = key[t];
+                    mv = kk[t];
+                }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const uint64_t ok = __shfl_xor_sync(0xffffffffu, mk, o);
+                const int ov = __shfl_xor_sync(0xffffffffu, mv, o);
+                if (ok > mk || (ok == mk && ov > mv)) {
+                    mk = ok;
+                    mv = ov;
+                }
+            }
+            tkey = mk;
+            tk = mv;
+        }
+        if (a.thr_key && lane == 0) {
+            a.thr_key[e] = tkey;
+            a.thr_k[e] = tk;
+        }
+        const int64_t r0 = a.rowptr[e];
+        const bool local = (e >= a.l0 && e < a.l1) && a.pk_jk != nullptr;
+        const int rsi = a.rowstart[i], rsj = a.rowstart[j];
+        int outpos = 0;
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            if (32 * t >= c) break;
+            const bool s1 = (sel >> t) & 1u;
+            const unsigned bal = __ballot_sync(0xffffffffu, s1);
+            if (s1) {
+                const int p = outpos + __popc(bal & lt);
+                const int k = kk[t];
+                a.apex[r0 + p] = k;
+                if (local) {
+                    const int ri_k = desc_rank(a.bm, a.bmprefix, a.nwords, i, k);
+                    const int rj_k = desc_rank(a.bm, a.bmprefix, a.nwords, j, k);
+                    const int eik = a.adj_eid[rsi + ri_k];
+                    const int ejk = a.adj_eid[rsj + rj_k];
+                    a.pk_ki[r0 - a.slot_base + p] = (uint32_t)eik | (i < k ? PK_SEL : 0u);
+                    a.pk_jk[r0 - a.slot_base + p] = (uint32_t)ejk | (j < k ? PK_SEL : 0u);
+                    if (a.rk_i) {
+                        a.rk_i[r0 - a.slot_base + p] = (uint16_t)ri_k;
+                        a.rk_j[r0 - a.slot_base + p] = (uint16_t)rj_k;
+                    }
+                }
+            }
+            outpos += __popc(bal);
+        }
+    }
+}
+
+template <int T>
+static int launch_fill_reg(desc_b200_handle* h, const FillArgs& fa) {
+    const size_t smem = (size_t)8 * 32 * T * sizeof(int);
+    CUDA_TRY(cudaFuncSetAttribute(k_fill_slots_reg<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ctas = T <= 8 ? 8 : (T <= 16 ? 4 : 2);
+    k_fill_slots_reg<T><<<DESC_SMS * ctas, 256, smem, h->stream>>>(fa);
+    KERNEL_CHECK(h);
+    return DESC_B200_OK;
+}
+
 // explicit cycle lists: apex is given; compute packed partner edges and validate
 __global__ void k_fill_explicit(FillArgs a, int* __restrict__ err) {
     const int lane = threadIdx.x & 31;
@@ -554,6 +718,13 @@ __global__ void k_fill_explicit(FillArgs a, int* __restrict__ err) {
                 a.rk_i[s - a.slot_base] = (uint16_t)ri_k;
                 a.rk_j[s - a.slot_base] = (uint16_t)rj_k;
             }
+            // a repeated apex within one edge (CEMP's with-replacement draw, CEMP.m:63) is legal for CEMP but not
+            // for the PGD kernels (their table updates assume distinct apices per edge): record it in err[3]
+            for (int64_t q = r0; q < s; q++)
+                if (a.apex[q] == k) {
+                    atomicOr(err + 3, 1);
+                    break;
+                }
         }
     }
 }
@@ -744,15 +915,16 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
         DESC_TRY(desc_allgather_ranges(h, h->codeg, sizeof(int), b));
     }
     // ---- histogram -> m_pos, max co-degree, sampling budget (DESC.m:36-43)
-    int* d_hist = nullptr;
-    CUDA_TRY(cudaMalloc(&d_hist, (size_t)(n + 1) * sizeof(int)));
+    DescTmp t_hist;
+    CUDA_TRY(t_hist.alloc((size_t)(n + 1) * sizeof(int)));
+    int* d_hist = t_hist.as<int>();
     CUDA_TRY(cudaMemsetAsync(d_hist, 0, (size_t)(n + 1) * sizeof(int), st));
     k_hist<<<gb, TB, 0, st>>>(h->codeg, m, d_hist);
     KERNEL_CHECK(h);
     std::vector<int> hist(n + 1);
     CUDA_TRY(cudaMemcpyAsync(hist.data(), d_hist, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    CUDA_TRY(cudaFree(d_hist));
+    t_hist.release();
     int64_t m_pos = 0;
     int maxc = 0;
     for (int c = 1; c <= n; c++)
@@ -763,8 +935,9 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
     h->m_pos = m_pos;
     h->max_codeg = maxc;
 
-    int* d_ns = nullptr;
-    CUDA_TRY(cudaMalloc(&d_ns, m * sizeof(int)));
+    DescTmp t_ns;   // (freed on the argument-error returns below as well)
+    CUDA_TRY(t_ns.alloc(m * sizeof(int)));
+    int* d_ns = t_ns.as<int>();
     CUDA_TRY(cudaMalloc(&h->rowptr, (m + 4) * sizeof(int64_t)));   // +3: 16-byte widened bulk copies (pgd_stream.cuh)
     const bool explicit_lists = cyc_ptr != nullptr;
     if (explicit_lists) {
@@ -823,7 +996,7 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
     }
     h->max_ns = std::min(h->n_sample, std::max(maxc, 1));
     if (explicit_lists) h->max_ns = h->n_sample;
-    CUDA_TRY(cudaFree(d_ns));
+    t_ns.release();
 
     // ---- shard: slot-balanced contiguous edge ranges
     h->shard_edges.assign(h->world + 1, 0);
@@ -911,9 +1084,12 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
             CUDA_TRY(cudaMemcpyAsync(h->apex, cyc_apex, h->m_cycle * sizeof(int), cudaMemcpyHostToDevice, st));
             k_fill_explicit<<<warp_grid, 256, 0, st>>>(fa, h->d_err);
             KERNEL_CHECK(h);
-            int herr = 0;
-            CUDA_TRY(cudaMemcpyAsync(&herr, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+            int herr4[4] = {0, 0, 0, 0};
+            CUDA_TRY(cudaMemcpyAsync(herr4, h->d_err, sizeof(herr4), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
+            const int herr = herr4[0];
+            h->has_dup_apex = herr4[3] != 0;
+            if (herr4[3]) CUDA_TRY(cudaMemsetAsync(h->d_err + 3, 0, sizeof(int), st));
             if (herr & ERRB_APEX) {
                 CUDA_TRY(cudaMemsetAsync(h->d_err, 0, sizeof(int), st));
                 desc_set_error("explicit cycle list contains an apex that is not a common neighbour");
@@ -936,8 +1112,21 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
             }
             fa.thr_key = h->thr_key;
             fa.thr_k = h->thr_k;
-            k_fill_slots<<<DESC_SMS * ctas_per_sm, wpb * 32, smem, st>>>(fa);
-            KERNEL_CHECK(h);
+            // register-resident selection for co-degrees up to 1024 (DESC_B200_FILL=generic forces the other kernel)
+            const char* fm = getenv("DESC_B200_FILL");
+            const bool generic = fm && strcmp(fm, "generic") == 0;
+            if (!generic && maxc <= 128) {
+                DESC_TRY(launch_fill_reg<4>(h, fa));
+            } else if (!generic && maxc <= 256) {
+                DESC_TRY(launch_fill_reg<8>(h, fa));
+            } else if (!generic && maxc <= 512) {
+                DESC_TRY(launch_fill_reg<16>(h, fa));
+            } else if (!generic && maxc <= 1024) {
+                DESC_TRY(launch_fill_reg<32>(h, fa));
+            } else {
+                k_fill_slots<<<DESC_SMS * ctas_per_sm, wpb * 32, smem, st>>>(fa);
+                KERNEL_CHECK(h);
+            }
             // every rank needs every edge's apex list (getters, explicit replays) and sampler threshold
             DESC_TRY(desc_allgather_ranges(h, h->apex, sizeof(int), h->shard_slots));
             DESC_TRY(desc_allgather_ranges(h, h->thr_key, sizeof(uint64_t), h->shard_edges));

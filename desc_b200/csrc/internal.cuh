@@ -13,8 +13,26 @@
 // ---- pooled device memory (pool.cu): every cudaMalloc / cudaFree of the library goes through it
 cudaError_t desc_pool_malloc(void** p, size_t bytes);
 cudaError_t desc_pool_free(void* p);
+cudaError_t desc_raw_malloc(void** p, size_t bytes);
+cudaError_t desc_raw_free(void* p);
 #define cudaMalloc(p, n) desc_pool_malloc((void**)(p), (n))
 #define cudaFree(p) desc_pool_free((void*)(p))
+
+// temporary device buffer that returns to the pool on every exit path (error returns included)
+struct DescTmp {
+    void* p = nullptr;
+    DescTmp() = default;
+    DescTmp(const DescTmp&) = delete;
+    DescTmp& operator=(const DescTmp&) = delete;
+    ~DescTmp() { release(); }
+    cudaError_t alloc(size_t bytes) { return desc_pool_malloc(&p, bytes); }
+    void release() {
+        if (p) desc_pool_free(p);
+        p = nullptr;
+    }
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
 
 // ---- error plumbing -----------------------------------------------------------------
 void desc_set_error(const char* fmt, ...);
@@ -72,6 +90,8 @@ struct desc_b200_handle {
     size_t comm_scratch_bytes = 0;
     int launches = 0;
     int collectives = 0;
+    void* sym = nullptr;        // peer-mapped symmetric region of this rank's communicator (comm.cu), or null
+    bool S_in_sym = false;      // S[0], S[1] live inside the symmetric region (not pool blocks)
 
     // graph ---------------------------------------------------------------------------
     int n = 0;
@@ -229,6 +249,14 @@ int desc_allgather_ranges(desc_b200_handle* h, void* buf, size_t elem_bytes,
                           const std::vector<int64_t>& bounds);
 int desc_reduce_to_owners(desc_b200_handle* h, double* buf, int width, const std::vector<int64_t>& bounds,
                           int tail, bool body_u64 = false);
+// Peer-memory exchanges of the PGD iteration (comm.cu): S[0], S[1] and a receive scratch live in a region that every
+// rank maps from every peer (CUDA IPC over NVLink); the exchanges are plain stores into the peers' memory plus a
+// flag barrier.  desc_sym_setup returns DESC_B200_OK with h->sym == nullptr when peer mapping is unavailable or
+// DESC_B200_COMM selects NCCL.
+int desc_sym_setup(desc_b200_handle* h, int64_t m, const std::vector<int64_t>& bounds);
+double* desc_sym_S_buffer(desc_b200_handle* h, int which);
+int desc_sym_allgather_S(desc_b200_handle* h, int which, const std::vector<int64_t>& bounds);
+int desc_sym_reduce_to_owners(desc_b200_handle* h, double* buf, const std::vector<int64_t>& bounds);
 
 // ---- device helpers -----------------------------------------------------------------
 #ifdef __CUDACC__

@@ -682,6 +682,7 @@ static int launch_stream_any(desc_b200_handle* h, const BlkArgs& a, int rule_kin
     ST_CASE(8, 4, 4)
     ST_CASE(8, 4, 2)
     ST_CASE(4, 8, 2)
+    ST_CASE(8, 2, 2)   // 16-edge tiles, 5 warps: three or four CTAs per SM (per-CTA prologue / drain overlap)
 #undef ST_CASE
     desc_set_error("DESC_B200_ST=%d,%d,%d,%d is not a compiled launch shape", epl, ncw, nsw, ctas);
     return DESC_B200_ERR_ARG;
@@ -908,6 +909,32 @@ static double step_size(const desc_b200_step_rule* r, int64_t t) {
     }
 }
 
+// a peer that died leaves the flag barrier of comm.cu with a timeout bit instead of a hang
+static int check_peer_barrier(desc_b200_handle* h) {
+    if (!h->sym) return DESC_B200_OK;
+    int e = 0;
+    CUDA_TRY(cudaMemcpy(&e, h->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e & 16) {
+        CUDA_TRY(cudaMemset(h->d_err, 0, sizeof(int)));
+        desc_set_error("multi-GPU exchange: a peer did not reach the barrier within the timeout");
+        return DESC_B200_ERR_NCCL;
+    }
+    return DESC_B200_OK;
+}
+
+// the two exchanges of a multi-GPU iteration: peer stores + flag barrier when the communicator has a peer-mapped
+// region (comm.cu), NCCL otherwise
+static int exchange_S(desc_b200_handle* h, int which) {
+    if (h->world <= 1) return DESC_B200_OK;
+    if (h->sym && h->S_in_sym) return desc_sym_allgather_S(h, which, h->shard_edges);
+    return desc_allgather_ranges(h, h->S[which], sizeof(double), h->shard_edges);
+}
+static int exchange_partner_sums(desc_b200_handle* h, int which, bool body_u64) {
+    if (h->world <= 1) return DESC_B200_OK;
+    if (h->sym && !body_u64) return desc_sym_reduce_to_owners(h, h->acc[which], h->shard_edges);
+    return desc_reduce_to_owners(h, h->acc[which], 2, h->shard_edges, 2, body_u64);
+}
+
 // The lane-per-edge path: state 0, the iterations with the reference's lagged early stop, the objective of the
 // last state; same bookkeeping kernels and history layout as the other paths.
 static int desc_pgd_ell(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int* iters_run) {
@@ -983,10 +1010,8 @@ static int desc_pgd_ell(desc_b200_handle* h, int iters, desc_b200_step_rule* rul
     a.acc_cur = nullptr;
     a.acc_next = h->acc[0];
     if (nt > 0) DESC_TRY((launch_ell<0, 1>(h, ea)));
-    if (h->world > 1) {
-        DESC_TRY(desc_allgather_ranges(h, h->S[0], sizeof(double), h->shard_edges));
-        DESC_TRY(desc_reduce_to_owners(h, h->acc[0], 2, h->shard_edges, 2, true));
-    }
+    DESC_TRY(exchange_S(h, 0));
+    DESC_TRY(exchange_partner_sums(h, 0, true));
 
     std::vector<cudaEvent_t>& evs = h->iter_events;
     while ((int)evs.size() < 5 * std::min(iters, 512)) {
@@ -1024,10 +1049,8 @@ static int desc_pgd_ell(desc_b200_handle* h, int iters, desc_b200_step_rule* rul
         k_pgd_partials<<<1, 256, 0, st>>>(h->pgd_partial, nt > 0 ? nv : 0, h->d_ctrl, h->acc[nxt] + 2 * m);
         KERNEL_CHECK(h);
         if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 3], st));
-        if (h->world > 1) {
-            DESC_TRY(desc_allgather_ranges(h, h->S[nxt], sizeof(double), h->shard_edges));
-            DESC_TRY(desc_reduce_to_owners(h, h->acc[nxt], 2, h->shard_edges, 2, true));
-        }
+        DESC_TRY(exchange_S(h, nxt));
+        DESC_TRY(exchange_partner_sums(h, nxt, true));
         if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 4], st));
         if (h->diag_on) DESC_TRY(desc_diag_record(h, t, h->S[nxt]));
         k_pgd_finalize<<<1, 1, 0, st>>>(h->acc[nxt] + 2 * m, t, 0, m, 1e-5, 30, h->d_hist, h->d_ctrl, h->d_ctrl_f);
@@ -1081,6 +1104,7 @@ static int desc_pgd_ell(desc_b200_handle* h, int iters, desc_b200_step_rule* rul
             cnt++;
         }
     }
+    DESC_TRY(check_peer_barrier(h));
     h->tm.pgd_pass1_ms = cnt > 0 ? s1 / cnt : 0.0;
     h->tm.pgd_pass2_ms = 0.0;
     h->tm.pgd_comm_ms = cnt > 0 ? sc / cnt : 0.0;
@@ -1098,6 +1122,11 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
         desc_set_error("bad iters / step rule");
         return DESC_B200_ERR_ARG;
     }
+    if (h->has_dup_apex) {
+        desc_set_error("the explicit cycle lists repeat an apex within an edge (a CEMP-style with-replacement draw): DESC's "
+                       "projected gradient needs distinct 3-cycles per edge (DESC.m:84 samples without replacement)");
+        return DESC_B200_ERR_STATE;
+    }
     cudaStream_t st = h->stream;
     const int64_t m = h->m;
     const int64_t nacc = 2 * m + 2;
@@ -1109,8 +1138,16 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
         const char* force = getenv("DESC_B200_PGD_PATH");
         if (force && strcmp(force, "blocked") == 0) stream = false;
     }
+    if (h->world > 1 && !h->sym && !h->S[0]) DESC_TRY(desc_sym_setup(h, m, h->shard_edges));
     for (int b = 0; b < 2; b++) {
-        if (!h->S[b]) CUDA_TRY(cudaMalloc(&h->S[b], (m + 4) * sizeof(double)));   // +4: 16-byte widened bulk copies
+        if (!h->S[b]) {
+            if (h->sym) {   // multi-GPU: S lives in the peer-mapped region, the all-gather is peer stores (comm.cu)
+                h->S[b] = desc_sym_S_buffer(h, b);
+                h->S_in_sym = true;
+            } else {
+                CUDA_TRY(cudaMalloc(&h->S[b], (m + 4) * sizeof(double)));   // +4: 16-byte widened bulk copies
+            }
+        }
         if (!h->acc[b]) CUDA_TRY(cudaMalloc(&h->acc[b], nacc * sizeof(double)));
     }
     if (!h->d_ctrl) {
@@ -1227,9 +1264,9 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
             if (!stream) DESC_TRY(launch_scatter<false>(h, ba, h->w[0], smem_sc));
         }
     }
-    if (h->world > 1) DESC_TRY(desc_allgather_ranges(h, h->S[0], sizeof(double), h->shard_edges));
+    DESC_TRY(exchange_S(h, 0));
     if (stream && h->n_slots > 0) DESC_TRY(launch_passb(h, ba, h->w[0]));   // needs every rank's S_0
-    if (h->world > 1) DESC_TRY(desc_reduce_to_owners(h, h->acc[0], 2, h->shard_edges, 2));
+    DESC_TRY(exchange_partner_sums(h, 0, false));
 
     // per-iteration kernel timing: events around the iteration kernels only
     std::vector<cudaEvent_t>& evs = h->iter_events;
@@ -1268,7 +1305,7 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
             ba.p = a;
             DESC_TRY(launch_stream_any(h, ba, adam ? 1 : 0));
             if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 1], st));
-            if (h->world > 1) DESC_TRY(desc_allgather_ranges(h, h->S[nxt], sizeof(double), h->shard_edges));
+            DESC_TRY(exchange_S(h, nxt));
             if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 2], st));
             DESC_TRY(launch_passb(h, ba, h->w[nxt]));
             k_pgd_partials<<<1, 256, 0, st>>>(h->pgd_partial, h->v_end - h->v_begin, h->d_ctrl, h->acc[nxt] + 2 * m);
@@ -1291,8 +1328,8 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
         }
         if (h->world > 1) {
             // a rank reads only the partner sums of its own edges: deliver each range's sum to its owner
-            DESC_TRY(desc_reduce_to_owners(h, h->acc[nxt], 2, h->shard_edges, 2));
-            if (!stream) DESC_TRY(desc_allgather_ranges(h, h->S[nxt], sizeof(double), h->shard_edges));
+            DESC_TRY(exchange_partner_sums(h, nxt, false));
+            if (!stream) DESC_TRY(exchange_S(h, nxt));
         }
         if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 4], st));
         if (h->diag_on) DESC_TRY(desc_diag_record(h, t, h->S[nxt]));   // make_plots branch, DESC.m:235-239
@@ -1354,6 +1391,7 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
             cnt++;
         }
     }
+    DESC_TRY(check_peer_barrier(h));
     h->tm.pgd_pass1_ms = cnt > 0 ? s1 / cnt : 0.0;
     h->tm.pgd_pass2_ms = cnt > 0 ? s2 / cnt : 0.0;
     h->tm.pgd_comm_ms = cnt > 0 ? sc / cnt : 0.0;

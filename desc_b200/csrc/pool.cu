@@ -81,3 +81,7 @@ extern "C" int desc_b200_trim(void) {
     cudaSetDevice(dev0);
     return DESC_B200_OK;
 }
+
+// raw allocations that never enter the pool (peer-mapped symmetric regions, comm.cu)
+cudaError_t desc_raw_malloc(void** p, size_t bytes) { return cudaMalloc(p, bytes); }
+cudaError_t desc_raw_free(void* p) { return cudaFree(p); }

@@ -1,7 +1,7 @@
 /*
  * desc_b200_mex.c -- thin MEX gateway: MATLAB host code -> C ABI (include/desc_b200.h) -> CUDA.
  *
- *   out = desc_b200_mex('solve', Ind, RijMat, iters, rule, n_sample, seed, want_R)
+ *   out = desc_b200_mex('solve', Ind, RijMat, iters, rule, n_sample, seed, want_R)     want_R: 0 | 1 (GCW) | 2 (GCW + refinement)
  *   out = desc_b200_mex('solve', Ind, RijMat, iters, rule, n_sample, seed, want_R, ErrVec, R_orig)
  *         (params.make_plots = true, DESC.m:235-239: adds out.diag = iters_run x 3
  *          [svec_errors, MSE_means, MSE_medians])
@@ -90,7 +90,9 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         rule.t = (int64_t)field_or(rs, "t", 0);
         const int n_sample = (int)mxGetScalar(prhs[5]);
         const uint64_t seed = (uint64_t)mxGetScalar(prhs[6]);
-        const int want_R = mxIsLogicalScalarTrue(prhs[7]) || (mxIsNumeric(prhs[7]) && mxGetScalar(prhs[7]) != 0);
+        /* want_R: false / 0 = S_vec only (DESC_PGD.m), true / 1 = + GCW rotations (DESC_init.m), 2 = + the refinement
+           stage DESC.m:265-312 on the SAME handle (DESC.m: no second upload of Ind / RijMat, no second graph build) */
+        const int want_R = mxIsLogicalScalarTrue(prhs[7]) ? 1 : (mxIsNumeric(prhs[7]) ? (int)mxGetScalar(prhs[7]) : 0);
 
         desc_b200_handle* h = NULL;
         fail_if(desc_b200_create(&h, 0, (int64_t)m, mxGetPr(prhs[1]), mxGetPr(prhs[2]), NULL), NULL);
@@ -126,6 +128,21 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
                                        mxGetPr(dg), &iters_run), h);
             if (want_R) fail_if(desc_b200_gcw(h, NULL, mxGetPr(R)), h);
         }
+        mxArray *Rref = NULL, *scores = NULL;
+        if (want_R >= 2) {   /* DESC.m:265-312 from the GCW rotations and S_vec that are still on the device */
+            mwSize dims[3] = {3, 3, 0};
+            dims[2] = n;
+            Rref = mxCreateNumericArray(3, dims, mxDOUBLE_CLASS, mxREAL);
+            mxArray* sc = mxCreateDoubleMatrix(1, 100, mxREAL);
+            int32_t lrun = 0;
+            fail_if(desc_b200_refine(h, NULL, NULL, mxGetPr(Rref), &lrun, mxGetPr(sc)), h);
+            scores = mxCreateDoubleMatrix(1, lrun, mxREAL);
+            for (int t = 0; t < lrun; t++) mxGetPr(scores)[t] = mxGetPr(sc)[t];
+            mxDestroyArray(sc);
+        } else {
+            Rref = mxCreateDoubleMatrix(0, 0, mxREAL);
+            scores = mxCreateDoubleMatrix(1, 0, mxREAL);
+        }
         fail_if(desc_b200_get_info(h, info), h);
         desc_b200_destroy(h);
 
@@ -142,8 +159,10 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
                 for (int c = 0; c < 3; c++) mxGetPr(dgT)[t + c * iters_run] = mxGetPr(dg)[3 * t + c];
             mxDestroyArray(dg);
         }
-        const char* fields[] = {"S_vec", "R_est", "hist", "iters_run", "t", "n_sample", "m_cycle", "diag"};
-        plhs[0] = mxCreateStructMatrix(1, 1, 8, fields);
+        const char* fields[] = {"S_vec", "R_est", "hist", "iters_run", "t", "n_sample", "m_cycle", "diag", "R_refined", "scores"};
+        plhs[0] = mxCreateStructMatrix(1, 1, 10, fields);
+        mxSetField(plhs[0], 0, "R_refined", Rref);
+        mxSetField(plhs[0], 0, "scores", scores);
         mxSetField(plhs[0], 0, "diag", dgT);
         mxSetField(plhs[0], 0, "S_vec", S);
         mxSetField(plhs[0], 0, "R_est", R);
@@ -262,7 +281,9 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
             mexErrMsgIdAndTxt("DESC:b200", "CEMP_parameters.reweighting must be a non-empty double vector");
         const int nsample = (int)mxGetScalar(prhs[5]);
         const uint64_t seed = (uint64_t)mxGetScalar(prhs[6]);
-        const int want_R = mxIsLogicalScalarTrue(prhs[7]) || (mxIsNumeric(prhs[7]) && mxGetScalar(prhs[7]) != 0);
+        /* want_R: false / 0 = S_vec only (DESC_PGD.m), true / 1 = + GCW rotations (DESC_init.m), 2 = + the refinement
+           stage DESC.m:265-312 on the SAME handle (DESC.m: no second upload of Ind / RijMat, no second graph build) */
+        const int want_R = mxIsLogicalScalarTrue(prhs[7]) ? 1 : (mxIsNumeric(prhs[7]) ? (int)mxGetScalar(prhs[7]) : 0);
         if (nsample <= 0) mexErrMsgIdAndTxt("DESC:b200", "CEMP_parameters.nsample must be positive");
         desc_b200_handle* h = NULL;
         fail_if(desc_b200_create(&h, 0, (int64_t)m, mxGetPr(prhs[1]), mxGetPr(prhs[2]), NULL), NULL);

@@ -437,6 +437,29 @@ def test_hybrid_gradient_rule_reuse_on_new_handle_is_rejected():
     assert rel_err(S, oS, floor=1e-12) <= RTOL
 
 
+def test_pgd_rejects_cycle_lists_with_repeated_apex():
+    """explicit lists may repeat an apex (CEMP's with-replacement draw, CEMP.m:63); CEMP runs on them, DESC's PGD
+    refuses (its kernels, like the reference's datasample without replacement, need distinct 3-cycles per edge)"""
+    mo = O.uniform_topology(60, 0.5, 0.2, 0.1, "uniform", rng=38)
+    inc = O.build_incidence(mo["Ind"], n_sample=8, seed=1)
+    cnt = np.zeros(inc.m, dtype=np.int64)
+    cnt[inc.pos_edges] = np.diff(inc.rowptr)
+    ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    apex = inc.k.astype(np.int32).copy()
+    e = int(np.flatnonzero(cnt >= 2)[0])
+    apex[ptr[e] + 1] = apex[ptr[e]]                                 # one repeated apex
+    with desc_b200.Solver(mo["Ind"], mo["RijMat"]) as s:
+        s.build_incidence(cycles=(ptr, apex))
+        s.cycle_inconsistency()
+        s.cemp(3, [1.0, 2.0, 4.0])                                  # legal for CEMP
+        with pytest.raises(desc_b200.DescError) as err:
+            s.pgd(3, desc_b200.ConstantStepSize(0.01))
+        assert err.value.code == _lib.ERR_STATE
+        s.build_incidence(cycles=(ptr, inc.k.astype(np.int32)))     # distinct again: accepted
+        s.cycle_inconsistency()
+        s.pgd(3, desc_b200.ConstantStepSize(0.01))
+
+
 _ORACLE_CACHE = {}
 
 
