@@ -999,22 +999,35 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
     t_ns.release();
 
     // ---- shard: slot-balanced contiguous edge ranges
-    h->shard_edges.assign(h->world + 1, 0);
+    // shard of this rank.  DESC_B200_FAKE_SHARD="r/N" (profiling only, single GPU): take the edge / slot range rank r
+    // of N would own, with no exchanges -- the kernels then do one rank's work of an N-GPU solve (results are NOT a
+    // solution: the other ranks' contributions are missing) so that they can be profiled with ncu on one GPU.
+    int sw = h->world, sr = h->rank;
+    if (h->world == 1) {
+        if (const char* fs = getenv("DESC_B200_FAKE_SHARD")) {
+            int r = 0, N = 1;
+            if (sscanf(fs, "%d/%d", &r, &N) == 2 && N >= 1 && N <= 64 && r >= 0 && r < N) {
+                sr = r;
+                sw = N;
+            }
+        }
+    }
+    h->shard_edges.assign(sw + 1, 0);
     {
         int64_t* d_b = nullptr;
-        CUDA_TRY(cudaMalloc(&d_b, (h->world + 1) * sizeof(int64_t)));
-        k_shard_bounds<<<1, 64, 0, st>>>(h->rowptr, m, h->m_cycle, h->world, d_b);
+        CUDA_TRY(cudaMalloc(&d_b, (sw + 1) * sizeof(int64_t)));
+        k_shard_bounds<<<1, 64, 0, st>>>(h->rowptr, m, h->m_cycle, sw, d_b);
         KERNEL_CHECK(h);
-        CUDA_TRY(cudaMemcpyAsync(h->shard_edges.data(), d_b, (h->world + 1) * sizeof(int64_t),
+        CUDA_TRY(cudaMemcpyAsync(h->shard_edges.data(), d_b, (sw + 1) * sizeof(int64_t),
                                  cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         CUDA_TRY(cudaFree(d_b));
     }
     // align shard boundaries to vertex blocks (all edges with the same smaller endpoint stay together)
     {
-        std::vector<int> v_of(h->world + 1, 0);
-        v_of[h->world] = n;
-        for (int r = 1; r < h->world; r++) {
+        std::vector<int> v_of(sw + 1, 0);
+        v_of[sw] = n;
+        for (int r = 1; r < sw; r++) {
             if (h->shard_edges[r] >= m) {
                 v_of[r] = n;
                 h->shard_edges[r] = m;
@@ -1023,18 +1036,18 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
                 h->shard_edges[r] = h->h_estart[v_of[r]];
             }
         }
-        h->v_begin = v_of[h->rank];
-        h->v_end = v_of[h->rank + 1];
+        h->v_begin = v_of[sr];
+        h->v_end = v_of[sr + 1];
     }
-    h->e_begin = h->shard_edges[h->rank];
-    h->e_end = h->shard_edges[h->rank + 1];
-    h->shard_slots.assign(h->world + 1, 0);
-    for (int r = 0; r <= h->world; r++)
+    h->e_begin = h->shard_edges[sr];
+    h->e_end = h->shard_edges[sr + 1];
+    h->shard_slots.assign(sw + 1, 0);
+    for (int r = 0; r <= sw; r++)
         CUDA_TRY(cudaMemcpyAsync(&h->shard_slots[r], h->rowptr + h->shard_edges[r], sizeof(int64_t),
                                  cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    h->slot_base = h->shard_slots[h->rank];
-    h->n_slots = h->shard_slots[h->rank + 1] - h->slot_base;
+    h->slot_base = h->shard_slots[sr];
+    h->n_slots = h->shard_slots[sr + 1] - h->slot_base;
 
     // + 16: the streamed PGD kernel widens its bulk copies to 16-byte boundaries (pgd_stream.cuh)
     const size_t ns_alloc = (size_t)std::max<int64_t>(h->n_slots, 1) + 16;
@@ -1071,6 +1084,10 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
     fa.rk_j = h->rk_j;
     fa.e0 = h->e_begin;
     fa.e1 = h->e_end;
+    if (sw != h->world) {   // profiling shard: no all-gather will deliver the other edges' lists / thresholds
+        fa.e0 = 0;
+        fa.e1 = m;
+    }
     fa.l0 = h->e_begin;
     fa.l1 = h->e_end;
     fa.slot_base = h->slot_base;

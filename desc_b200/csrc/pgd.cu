@@ -756,7 +756,10 @@ static int launch_passb(desc_b200_handle* h, const BlkArgs& a, const double* w_t
     // warps per CTA by the mean number of local in-edges per vertex (batches of PB_U edges per warp)
     const double per_cta = (double)(h->e_end - h->e_begin) / std::max(h->n, 1);
     int nw = per_cta >= 256 ? 8 : (per_cta >= 96 ? 4 : 2);
-    if (const char* o = getenv("DESC_B200_PB_WARPS")) nw = atoi(o);
+    if (const char* o = getenv("DESC_B200_PB_WARPS")) {
+        if (atoi(o) > 0) nw = atoi(o);
+    }
+    nw = nw >= 8 ? 8 : (nw >= 4 ? 4 : 2);
     const size_t smem = (size_t)(2 + nw) * a.tstride * sizeof(double);   // T_S, nw private tables, header tile
 #define PB_LAUNCH(NW)                                                                                              \
     {                                                                                                              \
