@@ -581,6 +581,7 @@ k_fill_slots_reg(FillArgs a) {
         for (int t = 0; t < T; t++) kk[t] = lane + 32 * t < c ? ck[lane + 32 * t] : -1;
         __syncwarp();
         const bool sample = c > a.n_sample;   // len==n_sample keeps everything (DESC.m:83)
+        const int tmax = (c + 31) >> 5;       // registers that hold candidates (warp-uniform): skip the empty ones
         uint32_t sel = 0u;                    // bit t: candidate of register t is in the slot list
 #pragma unroll
         for (int t = 0; t < T; t++) sel |= (kk[t] >= 0 ? 1u : 0u) << t;
@@ -589,7 +590,7 @@ k_fill_slots_reg(FillArgs a) {
         if (sample) {
             uint64_t key[T];
 #pragma unroll
-            for (int t = 0; t < T; t++) key[t] = kk[t] >= 0 ? desc_key(a.seed, (uint64_t)e, (uint64_t)kk[t]) : ~0ull;
+            for (int t = 0; t < T; t++) key[t] = (t < tmax && kk[t] >= 0) ? desc_key(a.seed, (uint64_t)e, (uint64_t)kk[t]) : ~0ull;
             uint32_t und = sel;
             sel = 0u;
             int need = a.n_sample, undc = c;
@@ -598,9 +599,11 @@ k_fill_slots_reg(FillArgs a) {
                 int cnt0 = 0;
 #pragma unroll
                 for (int t = 0; t < T; t++) {
-                    const bool p = ((und >> t) & 1u) && !((key[t] >> bit) & 1ull);
-                    cnt0 += __popc(__ballot_sync(0xffffffffu, p));
-                    zero |= (p ? 1u : 0u) << t;
+                    if (t < tmax) {
+                        const bool p = ((und >> t) & 1u) && !((key[t] >> bit) & 1ull);
+                        cnt0 += __popc(__ballot_sync(0xffffffffu, p));
+                        zero |= (p ? 1u : 0u) << t;
+                    }
                 }
                 if (cnt0 <= need) {   // all undecided keys with a 0 bit are among the smallest
                     sel |= zero;
@@ -617,17 +620,19 @@ k_fill_slots_reg(FillArgs a) {
             int taken = 0;
 #pragma unroll
             for (int t = 0; t < T; t++) {
-                const bool u = (und >> t) & 1u;
-                const unsigned bal = __ballot_sync(0xffffffffu, u);
-                if (u && taken + __popc(bal & lt) < need) sel |= 1u << t;
-                taken += __popc(bal);
+                if (t < tmax) {
+                    const bool u = (und >> t) & 1u;
+                    const unsigned bal = __ballot_sync(0xffffffffu, u);
+                    if (u && taken + __popc(bal & lt) < need) sel |= 1u << t;
+                    taken += __popc(bal);
+                }
             }
             // threshold = largest selected (key, apex)
             uint64_t mk = 0ull;
             int mv = -1;
 #pragma unroll
             for (int t = 0; t < T; t++)
-                if (((sel >> t) & 1u) && (key[t] > mk || (key[t] == mk && kk[t] > mv))) {
+                if (t < tmax && ((sel >> t) & 1u) && (key[t] > mk || (key[t] == mk && kk[t] > mv))) {
                     mk = key[t];
                     mv = kk[t];
                 }

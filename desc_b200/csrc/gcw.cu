@@ -96,7 +96,7 @@ __global__ void k_gcw_init(double* __restrict__ X, int64_t n9) {
 // wavefronts per record instead of 9) -- and a per-warp staging buffer (stride 9 doubles, conflict-free) hands the
 // record to the lane that owns the entry.  coef is kept in adjacency order (coalesced).
 #define SPMV_WARPS 8
-__global__ void __launch_bounds__(SPMV_WARPS * 32)
+__global__ void __launch_bounds__(SPMV_WARPS * 32, 3)
 k_gcw_spmv(const int* __restrict__ rowstart, const int* __restrict__ adj_nbr,
            const int* __restrict__ adj_eid, const double* __restrict__ Rij,
            const double* __restrict__ coef_adj, const double* __restrict__ X, double* __restrict__ Y,

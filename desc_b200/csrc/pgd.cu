@@ -675,7 +675,9 @@ static int launch_stream_ns(desc_b200_handle* h, const BlkArgs& a, int rule_kind
 // DESC_B200_ST="<slots per lane>,<compute warps>,<scatter warps>,<CTAs per SM>" picks another
 // compiled launch shape (experiments).
 static int launch_stream_any(desc_b200_handle* h, const BlkArgs& a, int rule_kind, bool dry = false) {
-    int epl = 8, ncw = 4, nsw = 4, ctas = 2;   // best of the shapes measured at cfg 4 (profiles/README.md)
+    // best of the shapes measured at cfg 4 (profiles/README.md): 16-edge tiles, 2 compute + 2 scatter warps and four
+    // CTAs per SM -- smaller CTAs overlap each other's per-vertex prologue / drain (round 2: 1.29 -> 1.24 ms)
+    int epl = 8, ncw = 2, nsw = 2, ctas = 4;
     if (const char* o = getenv("DESC_B200_ST")) sscanf(o, "%d,%d,%d,%d", &epl, &ncw, &nsw, &ctas);
 #define ST_CASE(E, C, S) \
     if (epl == E && ncw == C && nsw == S) return launch_stream_ns<E, C, S>(h, a, rule_kind, ctas, dry);
@@ -755,7 +757,9 @@ static int launch_passb(desc_b200_handle* h, const BlkArgs& a, const double* w_t
     }
     // warps per CTA by the mean number of local in-edges per vertex (batches of PB_U edges per warp)
     const double per_cta = (double)(h->e_end - h->e_begin) / std::max(h->n, 1);
-    int nw = per_cta >= 256 ? 8 : (per_cta >= 96 ? 4 : 2);
+    // (2-warp CTAs were used for the small per-vertex work of 4-8 GPU shards; measured on one rank's share of an
+    // 8-GPU solve, 4 warps are faster there too: 0.476 -> 0.438 ms, profiles/README.md round 2)
+    int nw = per_cta >= 256 ? 8 : 4;
     if (const char* o = getenv("DESC_B200_PB_WARPS")) {
         if (atoi(o) > 0) nw = atoi(o);
     }

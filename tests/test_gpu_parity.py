@@ -473,7 +473,7 @@ def _cached_case(n, p, rng, lr, iters, ns, seed):
     return _ORACLE_CACHE[key]
 
 
-@pytest.mark.parametrize("shape", ["8,4,4,2", "8,4,2,2", "4,8,2,2"])
+@pytest.mark.parametrize("shape", ["8,2,2,4", "8,4,4,2", "8,4,2,2", "4,8,2,2"])
 @pytest.mark.parametrize("ns", [0, 45, 100])
 def test_streamed_path_launch_shapes_and_slot_list_lengths(monkeypatch, shape, ns):
     """every compiled (slots per lane, compute warps, scatter warps) shape of the TMA-streamed kernel, with
