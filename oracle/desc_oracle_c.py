@@ -243,8 +243,9 @@ def gcw(Ind, RijMat, S_vec, power=1.5, threads=0, graph=None, timings=None):
     return out
 
 
-def DESC_init(Ind, RijMat, params, n_sample=None, seed=0, threads=0, full=False):
-    """Algorithms/DESC_init.m:14 on the C port; ``full`` returns every intermediate and the per-stage seconds."""
+def DESC_init(Ind, RijMat, params, n_sample=None, seed=0, threads=0, full=False, want_R=True):
+    """Algorithms/DESC_init.m:14 on the C port (``want_R=False``: DESC_PGD.m:14, no GCW); ``full`` returns every
+    intermediate and the per-stage seconds."""
     tm = {}
     t0 = time.perf_counter()
     g = Graph(Ind)
@@ -253,7 +254,10 @@ def DESC_init(Ind, RijMat, params, n_sample=None, seed=0, threads=0, full=False)
     S0 = cycle_inconsistency(inc, RijMat, threads=threads, timings=tm)
     S_vec, hist, iters_run, w = pgd(inc, S0, int(params["iters"]), params["Gradient"], threads=threads, return_w=True,
                                     timings=tm)
-    R = gcw(Ind, RijMat, S_vec, threads=threads, graph=g, timings=tm)
+    R = None
+    tm["gcw_s"] = 0.0
+    if want_R:
+        R = gcw(Ind, RijMat, S_vec, threads=threads, graph=g, timings=tm)
     if full:
         return dict(R=R, S_vec=S_vec, hist=hist, iters_run=iters_run, w=w, S0=S0, inc=inc, timings=tm)
     return R, S_vec
