@@ -856,6 +856,54 @@ __global__ void k_shard_bounds(const int64_t* __restrict__ rowptr, int64_t m, in
     bounds[r] = lo;
 }
 
+// rowptr at the first edge of every vertex block (cumulative slots per vertex), n+1 values
+__global__ void k_vertex_slots(const int64_t* __restrict__ rowptr, const int* __restrict__ estart, int n,
+                               int64_t* __restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v <= n) out[v] = rowptr[estart[v]];
+}
+
+// Vertex-aligned shard boundaries from a cost model instead of equal slot counts (round 2).  Per-rank times fitted
+// on 2 and 8 B200 at cfg 4 (profiles/README.md): pass 1 costs its slots plus ~4.5 slot-equivalents per adjacency
+// entry of every LOCAL vertex block (table prologue / flush of the CTA), pass 2 costs its slots (x1.2) plus ~3.9
+// slot-equivalents per adjacency entry of every vertex ABOVE the rank's first vertex (each of them gets a CTA with
+// a full table).  The passes are separated by the exchange of S, so the iteration takes max(pass 1) + max(pass 2):
+// coordinate descent on the N-1 boundaries from the slot-balanced start.  cs[v] = cumulative slots before vertex
+// block v, ca[v] = cumulative adjacency entries (rowstart).
+static void cost_model_bounds(const std::vector<int64_t>& cs, const std::vector<int>& ca, int n, int W,
+                              std::vector<int>& vb) {
+    const double k1 = 4.5, k2 = 3.9, b2 = 1.2;
+    auto objective = [&](const std::vector<int>& b) {
+        double m1 = 0.0, m2 = 0.0;
+        for (int r = 0; r < W; r++) {
+            const double slots = (double)(cs[b[r + 1]] - cs[b[r]]);
+            m1 = std::max(m1, slots + k1 * (double)(ca[b[r + 1]] - ca[b[r]]));
+            m2 = std::max(m2, slots > 0.0 ? b2 * slots + k2 * (double)(ca[n] - ca[b[r]]) : 0.0);
+        }
+        return m1 + m2;
+    };
+    double best = objective(vb);
+    for (int step = std::max(1, n / 16); step >= 1; step /= 2) {
+        bool moved = true;
+        for (int sweep = 0; sweep < 64 && moved; sweep++) {
+            moved = false;
+            for (int r = 1; r < W; r++) {
+                for (int dir = -1; dir <= 1; dir += 2) {
+                    std::vector<int> t = vb;
+                    t[r] = std::min(std::max(t[r] + dir * step, t[r - 1]), t[r + 1]);
+                    if (t[r] == vb[r]) continue;
+                    const double o = objective(t);
+                    if (o < best * (1.0 - 1e-9)) {
+                        best = o;
+                        vb = t;
+                        moved = true;
+                    }
+                }
+            }
+        }
+    }
+}
+
 static void free_incidence(desc_b200_handle* h) {
     cudaFree(h->rowptr);
     cudaFree(h->apex);
@@ -1040,6 +1088,21 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
                 CUDA_TRY(cudaMemcpy(&v_of[r], h->ei + h->shard_edges[r], sizeof(int), cudaMemcpyDeviceToHost));
                 h->shard_edges[r] = h->h_estart[v_of[r]];
             }
+        }
+        // cost-model boundaries (DESC_B200_SHARD=slots keeps the slot-balanced ones)
+        const char* sm = getenv("DESC_B200_SHARD");
+        if (sw > 1 && !(sm && strcmp(sm, "slots") == 0) && h->blocked_ok) {
+            DescTmp t_cs;
+            CUDA_TRY(t_cs.alloc((size_t)(n + 1) * sizeof(int64_t)));
+            k_vertex_slots<<<(n + 1 + 255) / 256, 256, 0, st>>>(h->rowptr, h->estart, n, t_cs.as<int64_t>());
+            KERNEL_CHECK(h);
+            std::vector<int64_t> cs(n + 1);
+            std::vector<int> ca(n + 1);
+            CUDA_TRY(cudaMemcpyAsync(cs.data(), t_cs.p, (size_t)(n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(ca.data(), h->rowstart, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            cost_model_bounds(cs, ca, n, sw, v_of);
+            for (int r = 1; r < sw; r++) h->shard_edges[r] = h->h_estart[v_of[r]];
         }
         h->v_begin = v_of[sr];
         h->v_end = v_of[sr + 1];

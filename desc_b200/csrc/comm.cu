@@ -588,6 +588,12 @@ int desc_sym_setup(desc_b200_handle* h, int64_t m, const std::vector<int64_t>& b
     return DESC_B200_OK;
 }
 
+// flag barrier over all ranks of the handle's communicator (no-op without a peer-mapped region)
+int desc_sym_barrier(desc_b200_handle* h) {
+    if (!h->sym) return DESC_B200_OK;
+    return sym_barrier(h, (SymRegion*)h->sym);
+}
+
 static double* sym_S(SymRegion* R, int which) {
     return reinterpret_cast<double*>(R->local + SYM_FLAG_BYTES) + (int64_t)which * R->cap_m;
 }

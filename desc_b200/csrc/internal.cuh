@@ -255,6 +255,7 @@ int desc_reduce_to_owners(desc_b200_handle* h, double* buf, int width, const std
 // DESC_B200_COMM selects NCCL.
 int desc_sym_setup(desc_b200_handle* h, int64_t m, const std::vector<int64_t>& bounds);
 double* desc_sym_S_buffer(desc_b200_handle* h, int which);
+int desc_sym_barrier(desc_b200_handle* h);
 int desc_sym_allgather_S(desc_b200_handle* h, int which, const std::vector<int64_t>& bounds);
 int desc_sym_reduce_to_owners(desc_b200_handle* h, double* buf, const std::vector<int64_t>& bounds);
 

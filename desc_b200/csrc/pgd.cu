@@ -1205,6 +1205,9 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
         KERNEL_CHECK(h);
         k_fill_double<<<gb, 256, 0, st>>>(h->S[1], m, 1.0);
         KERNEL_CHECK(h);
+        // S lives in peer-mapped memory on multi-GPU handles: no rank may push its first S slice into this rank's
+        // buffers before the fills above have run (a faster peer's slice would be overwritten with ones)
+        if (h->S_in_sym) DESC_TRY(desc_sym_barrier(h));
     }
     if (use_ell) return desc_pgd_ell(h, iters, rule, iters_run);
     PgdArgs a;
