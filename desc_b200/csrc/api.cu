@@ -154,15 +154,35 @@ int desc_b200_create(desc_b200_handle** out, int32_t n, int64_t m, const double*
         }
     auto body = [&]() -> int {
         const double* d_Ind = Ind;
+        DescTmp t_ind;   // device copy of Ind: only needed until the graph is set up (freed on error returns too)
         double* d_Ind_owned = nullptr;
         if (o.flags & DESC_B200_INPUTS_ON_DEVICE) {
             h->Rij = RijMat;
         } else {
             StageTimer t(h, &h->tm.h2d_ms);
-            CUDA_TRY(cudaMalloc(&d_Ind_owned, 2 * m * sizeof(double)));
+            CUDA_TRY(t_ind.alloc(2 * m * sizeof(double)));
+            d_Ind_owned = t_ind.as<double>();
             CUDA_TRY(cudaMalloc(&h->Rij_owned, 9 * m * sizeof(double)));
-            CUDA_TRY(cudaMemcpyAsync(d_Ind_owned, Ind, 2 * m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-            CUDA_TRY(cudaMemcpyAsync(h->Rij_owned, RijMat, 9 * m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            if (h->world > 1) {
+                // every rank was given the same host arrays (the contract of a sharded solve): each uploads 1/world of
+                // them over PCIe and the slices are all-gathered over NVLink -- with 8 ranks on one host the full
+                // upload per rank (440 MB at cfg 4, 8 x in parallel through one host) cost ~20 ms per solve
+                DESC_TRY(desc_comm_init(h, o.nccl_id));
+                std::vector<int64_t> b(h->world + 1);
+                for (int r = 0; r <= h->world; r++) b[r] = (m * r) / h->world;
+                const int64_t b0 = b[h->rank], cnt = b[h->rank + 1] - b[h->rank];
+                if (cnt > 0) {
+                    CUDA_TRY(cudaMemcpyAsync(d_Ind_owned + b0, Ind + b0, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+                    CUDA_TRY(cudaMemcpyAsync(d_Ind_owned + m + b0, Ind + m + b0, cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+                    CUDA_TRY(cudaMemcpyAsync(h->Rij_owned + 9 * b0, RijMat + 9 * b0, 9 * cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+                }
+                DESC_TRY(desc_allgather_ranges(h, d_Ind_owned, sizeof(double), b));
+                DESC_TRY(desc_allgather_ranges(h, d_Ind_owned + m, sizeof(double), b));
+                DESC_TRY(desc_allgather_ranges(h, h->Rij_owned, 9 * sizeof(double), b));
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(d_Ind_owned, Ind, 2 * m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+                CUDA_TRY(cudaMemcpyAsync(h->Rij_owned, RijMat, 9 * m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            }
             DESC_TRY(t.stop());
             d_Ind = d_Ind_owned;
             h->Rij = h->Rij_owned;
@@ -173,9 +193,9 @@ int desc_b200_create(desc_b200_handle** out, int32_t n, int64_t m, const double*
             r = desc_graph_setup(h, d_Ind);
             if (r == DESC_B200_OK) r = t.stop();
         }
-        if (d_Ind_owned) cudaFree(d_Ind_owned);
+        t_ind.release();
         DESC_TRY(r);
-        DESC_TRY(desc_comm_init(h, o.nccl_id));
+        if (!h->comm) DESC_TRY(desc_comm_init(h, o.nccl_id));
         return DESC_B200_OK;
     };
     rc = body();

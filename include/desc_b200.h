@@ -58,7 +58,9 @@ typedef struct desc_b200_opts {
     uint32_t flags;
     void* stream;         /* cudaStream_t to run on; NULL = the library creates its own      */
     /* multi-GPU: one process per GPU.  world<=1 means single GPU.  nccl_id is the 128-byte
-       ncclUniqueId made by desc_b200_nccl_unique_id() on rank 0 and broadcast by the host. */
+       ncclUniqueId made by desc_b200_nccl_unique_id() on rank 0 and broadcast by the host.
+       Every rank must pass the SAME Ind / RijMat: with host inputs each rank uploads 1/world of
+       them and the slices are all-gathered over NVLink.                                        */
     int32_t rank;
     int32_t world;
     const void* nccl_id;
