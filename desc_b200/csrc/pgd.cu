@@ -571,19 +571,22 @@ k_pgd_scatter(BlkArgs a, const double* __restrict__ w) {
 }
 
 // fixed-order reduction of the per-CTA partials into red[0] (objective) and red[1] (change)
-__global__ void k_pgd_partials(const double* __restrict__ partial, int nblocks, const int* __restrict__ ctrl,
-                               double* __restrict__ red) {
+#define PGD_PART_TB 1024
+__global__ void __launch_bounds__(PGD_PART_TB)
+k_pgd_partials(const double* __restrict__ partial, int nblocks, const int* __restrict__ ctrl,
+               double* __restrict__ red) {
     if (ctrl[0]) return;
-    __shared__ double sh[2][256];
+    __shared__ double sh[2][PGD_PART_TB];
     double o = 0.0, c = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += 256) {
-        o += partial[2 * b];
-        c += partial[2 * b + 1];
+    for (int b = threadIdx.x; b < nblocks; b += PGD_PART_TB) {
+        const double2 v = reinterpret_cast<const double2*>(partial)[b];
+        o += v.x;
+        c += v.y;
     }
     sh[0][threadIdx.x] = o;
     sh[1][threadIdx.x] = c;
     __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
+    for (int off = PGD_PART_TB / 2; off > 0; off >>= 1) {
         if (threadIdx.x < off) {
             sh[0][threadIdx.x] += sh[0][threadIdx.x + off];
             sh[1][threadIdx.x] += sh[1][threadIdx.x + off];
@@ -1053,7 +1056,7 @@ static int desc_pgd_ell(desc_b200_handle* h, int iters, desc_b200_step_rule* rul
                 DESC_TRY((launch_ell<0, 0>(h, ea)));
         }
         if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 1], st));
-        k_pgd_partials<<<1, 256, 0, st>>>(h->pgd_partial, nt > 0 ? nv : 0, h->d_ctrl, h->acc[nxt] + 2 * m);
+        k_pgd_partials<<<1, PGD_PART_TB, 0, st>>>(h->pgd_partial, nt > 0 ? nv : 0, h->d_ctrl, h->acc[nxt] + 2 * m);
         KERNEL_CHECK(h);
         if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 3], st));
         DESC_TRY(exchange_S(h, nxt));
@@ -1080,7 +1083,7 @@ static int desc_pgd_ell(desc_b200_handle* h, int iters, desc_b200_step_rule* rul
         a.acc_cur = h->acc[cur];
         a.acc_next = h->acc[nxt];
         if (nt > 0) DESC_TRY((launch_ell<0, 2>(h, ea)));
-        k_pgd_partials<<<1, 256, 0, st>>>(h->pgd_partial, nt > 0 ? nv : 0, h->d_ctrl, h->acc[nxt] + 2 * m);
+        k_pgd_partials<<<1, PGD_PART_TB, 0, st>>>(h->pgd_partial, nt > 0 ? nv : 0, h->d_ctrl, h->acc[nxt] + 2 * m);
         KERNEL_CHECK(h);
         if (h->world > 1) DESC_TRY(desc_allreduce_sum(h, h->acc[nxt] + 2 * m, 2));
         k_pgd_finalize<<<1, 1, 0, st>>>(h->acc[nxt] + 2 * m, iters, 1, m, 1e-5, 30, h->d_hist, h->d_ctrl, h->d_ctrl_f);
@@ -1318,13 +1321,13 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
             DESC_TRY(exchange_S(h, nxt));
             if (timed) CUDA_TRY(cudaEventRecord(evs[5 * (t - 1) + 2], st));
             DESC_TRY(launch_passb(h, ba, h->w[nxt]));
-            k_pgd_partials<<<1, 256, 0, st>>>(h->pgd_partial, h->v_end - h->v_begin, h->d_ctrl, h->acc[nxt] + 2 * m);
+            k_pgd_partials<<<1, PGD_PART_TB, 0, st>>>(h->pgd_partial, h->v_end - h->v_begin, h->d_ctrl, h->acc[nxt] + 2 * m);
             KERNEL_CHECK(h);
         } else if (blocked) {
             ba.p = a;
             DESC_TRY(launch_block_any(h, ba, adam ? 1 : 0, smem_blk));
             DESC_TRY(launch_scatter<false>(h, ba, h->w[nxt], smem_sc));
-            k_pgd_partials<<<1, 256, 0, st>>>(h->pgd_partial, h->v_end - h->v_begin, h->d_ctrl, h->acc[nxt] + 2 * m);
+            k_pgd_partials<<<1, PGD_PART_TB, 0, st>>>(h->pgd_partial, h->v_end - h->v_begin, h->d_ctrl, h->acc[nxt] + 2 * m);
             KERNEL_CHECK(h);
         } else {
             DESC_TRY(launch_iter_any(h, a, adam ? 1 : 0));
@@ -1372,7 +1375,7 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
                 k_pgd_obj<32><<<aux_grid, 256, 0, st>>>(a, part);
             KERNEL_CHECK(h);
             if (blocked) {
-                k_pgd_partials<<<1, 256, 0, st>>>(h->pgd_partial, aux_grid, h->d_ctrl, h->acc[nxt] + 2 * m);
+                k_pgd_partials<<<1, PGD_PART_TB, 0, st>>>(h->pgd_partial, aux_grid, h->d_ctrl, h->acc[nxt] + 2 * m);
                 KERNEL_CHECK(h);
             }
         }
