@@ -71,7 +71,11 @@ typedef struct desc_b200_opts {
    kind 1: Utils/PiecewiseStepSize.m:13-18  t++; step = -lr/(fix(t/decay_interval)+1)*grad
    kind 2: Utils/HybridGradient.m:23-41     strategy 0: Adam(beta_1,beta_2,eps 1e-8, bias corrected)
                                             strategy 1: step = -100*lr/(fix(t/decay_interval)+1)*grad
-   `t` is the object's call counter on entry; on return it has advanced by iters_run.       */
+   `t` is the object's call counter on entry; on return it has advanced by iters_run.
+   Adam's moments m_t / v_t (m_cycle doubles each) live on the device inside the handle and are zeroed
+   when t == 0 (HybridGradient.m:24-27).  A rule with t > 0 therefore continues only on the handle that
+   ran its earlier steps; on any other handle (or after build_incidence, or after a run that the early
+   stop ended: its moments are one step ahead of the reported state) pgd returns DESC_B200_ERR_STATE.  */
 typedef struct desc_b200_step_rule {
     int32_t kind;
     int32_t strategy;
