@@ -514,8 +514,12 @@ def run_gpu(args, wl):
                   "d_ijk": stage(72.0 * info["m"] + 20.0 * local_slots + 4.0 * local_edges, tm["cycle_ms"])}
         if tm.get("gcw_spmv_ms", 0) > 0:
             stages["gcw_spmv"] = stage(88.0 * info["m"] + 144.0 * n, tm["gcw_spmv_ms"])
+        two_pass = tm.get("pgd_pass2_ms", 0.0) > 0.0
         roofline = {"bound": "hbm",
-                    "kernel": "PGD iteration = k_pgd_stream (update, smaller endpoints) + k_pgd_passb (tables, larger endpoints)",
+                    "kernel": ("PGD iteration = k_pgd_stream (update, smaller endpoints) + k_pgd_passb (tables, larger endpoints)"
+                               if two_pass else
+                               "PGD iteration = k_pgd_block (update) + k_pgd_scatter (tables): the direct-load kernels the "
+                               "library picks for sparse graphs (fewer than 100 own edges per vertex), timed as one span"),
                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": iter_ms,

@@ -1206,7 +1206,9 @@ int desc_build_incidence_impl(desc_b200_handle* h, int n_sample_req, uint64_t se
                 DESC_TRY(launch_fill_reg<8>(h, fa));
             } else if (!generic && maxc <= 512) {
                 DESC_TRY(launch_fill_reg<16>(h, fa));
-            } else if (!generic && maxc <= 1024) {
+            } else if (!generic && maxc <= 1024 && fm && strcmp(fm, "reg32") == 0) {
+                // 32 candidate registers per lane need 242 registers per thread: measured 43 ms against the 11.5 ms
+                // of the shared-memory kernel at cfg 3 (co-degrees ~500), so this shape is opt-in only
                 DESC_TRY(launch_fill_reg<32>(h, fa));
             } else {
                 k_fill_slots<<<DESC_SMS * ctas_per_sm, wpb * 32, smem, st>>>(fa);

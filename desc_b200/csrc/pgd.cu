@@ -1147,6 +1147,10 @@ int desc_pgd_impl(desc_b200_handle* h, int iters, desc_b200_step_rule* rule, int
     {
         const char* force = getenv("DESC_B200_PGD_PATH");
         if (force && strcmp(force, "blocked") == 0) stream = false;
+        // sparse graphs (cfg 5's ring: 50 own edges per vertex) make tens of thousands of tiny vertex blocks, and the
+        // streamed kernel pays ~31 ns of ring / table prologue and drain per block: measured 2.61 ms per iteration
+        // against 2.12 ms of the direct-load blocked kernels there (single GPU; profiles/README.md round 2)
+        if (!force && h->world == 1 && h->m < 100 * (int64_t)h->n) stream = false;
     }
     if (h->world > 1 && !h->sym && !h->S[0]) DESC_TRY(desc_sym_setup(h, m, h->shard_edges));
     for (int b = 0; b < 2; b++) {
