@@ -102,19 +102,63 @@ def captured_traffic(workload, world):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU every 100 ms while the timed region runs (what the profiling recipe's
+    `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` line reports), read through NVML in a
+    background thread of this process.  A looping `nvidia-smi` child was used first: its start-up and its much larger
+    per-sample query set stalled driver calls of the benchmarked process (tens of ms per step on the short cfg-2 /
+    cfg-5 steps); it remains the fallback when the NVML binding cannot be imported."""
+    NAMES = [("hw_slowdown", "HwSlowdown"), ("hw_thermal_slowdown", "HwThermalSlowdown"),
+             ("sw_thermal_slowdown", "SwThermalSlowdown"), ("sw_power_cap", "SwPowerCap")]
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        import threading
         self.p = None
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.via = "nvml"
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].strip().isdigit() else index
+            hdl = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            masks = [(nm, getattr(pynvml, "nvmlClocksEventReason" + sfx, None) or
+                      getattr(pynvml, "nvmlClocksThrottleReason" + sfx)) for nm, sfx in self.NAMES]
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(hdl, pynvml.NVML_CLOCK_SM)))
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(hdl, pynvml.NVML_CLOCK_SM)))
+                        r = int(get_reasons(hdl))
+                        for nm, mask in masks:
+                            if r & mask:
+                                self.reasons.add(nm)
+                    except Exception:
+                        pass
+                    self._stop.wait(0.1)
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
         except Exception:
-            self.p = None
+            self.via = "nvidia-smi"
+            try:
+                self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                           "--format=csv,noheader,nounits", "-lms", "100"],
+                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except Exception:
+                self.p = None
 
     def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "via": "nvml"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -139,7 +183,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "via": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------
