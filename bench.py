@@ -117,6 +117,7 @@ class ClockSampler:
         self.p = None
         self.sm, self.mx, self.reasons = [], [], set()
         self.via = "nvml"
+        self.period = float(os.environ.get("DESC_BENCH_CLOCK_PERIOD", "0.1"))   # seconds between samples
         self._stop = threading.Event()
         self._thread = None
         try:
@@ -141,7 +142,7 @@ class ClockSampler:
                                 self.reasons.add(nm)
                     except Exception:
                         pass
-                    self._stop.wait(0.1)
+                    self._stop.wait(self.period)
             self._thread = threading.Thread(target=loop, daemon=True)
             self._thread.start()
         except Exception:
@@ -433,14 +434,28 @@ def run_gpu(args, wl):
             s.close()
 
     def timed(fn, steps):
+        import gc
+        gc.collect()
+        gc.disable()            # no collector pauses of the host inside the timed region
+        try:
+            return _timed(fn, steps)
+        finally:
+            gc.enable()
+
+    def _timed(fn, steps):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
         launches = 0
+        trace = os.environ.get("DESC_BENCH_TRACE") == "1"   # diagnostics: host wall time of every step (adds a sync)
         for _ in range(steps):
+            t0 = time.perf_counter()
             fn()
+            if trace:
+                torch.cuda.synchronize(dev)
+                sys.stderr.write("step %s: %.1f ms\n" % (fn.__name__, 1e3 * (time.perf_counter() - t0)))
             launches += state.get("timings", {}).get("total_launches", 0)
         ev1.record(stream)
         torch.cuda.synchronize(dev)
@@ -453,7 +468,7 @@ def run_gpu(args, wl):
 
     # the clock sampler starts BEFORE the warm-up: nvidia-smi's own start-up (NVML init) must not fall into the timed
     # region (it cost ~10 ms per step on the 35 ms steps of cfg 2)
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and os.environ.get("DESC_BENCH_NO_CLOCKS") != "1" else None
     for _ in range(args.warmup):
         step_resident()
     ms_total, launches = timed(step_resident, args.steps)
@@ -558,7 +573,7 @@ def run_gpu(args, wl):
                   "d_ijk": stage(72.0 * info["m"] + 20.0 * local_slots + 4.0 * local_edges, tm["cycle_ms"])}
         if tm.get("gcw_spmv_ms", 0) > 0:
             stages["gcw_spmv"] = stage(88.0 * info["m"] + 144.0 * n, tm["gcw_spmv_ms"])
-        two_pass = tm.get("pgd_pass2_ms", 0.0) > 0.0
+        two_pass = tm.get("pgd_pass2_ms", 0.0) > 0.05 * max(tm.get("pgd_pass1_ms", 0.0), 1e-9)
         roofline = {"bound": "hbm",
                     "kernel": ("PGD iteration = k_pgd_stream (update, smaller endpoints) + k_pgd_passb (tables, larger endpoints)"
                                if two_pass else
