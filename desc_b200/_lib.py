@@ -28,7 +28,7 @@ SYMBOLS = [
     "desc_b200_cemp", "desc_b200_cemp_gcw", "desc_b200_cycle_reweight", "desc_b200_rotation_alignment",
     "desc_b200_pgd_diag", "desc_b200_mst_init", "desc_b200_mpls_refine", "desc_b200_spectral",
     "desc_b200_generate", "desc_b200_model_destroy", "desc_b200_model_info", "desc_b200_model_fetch",
-    "desc_b200_model_device",
+    "desc_b200_model_device", "desc_b200_plan_shards",
 ]
 
 

@@ -904,6 +904,33 @@ static void cost_model_bounds(const std::vector<int64_t>& cs, const std::vector<
     }
 }
 
+// The shard plan as a host-only entry point (no device needed): CPU tests pin the rule, and a caller can ask where
+// the boundaries of a world would fall.  cum_slots[v] = slots of the vertex blocks before v (n+1 values),
+// cum_adj[v] = adjacency entries before v (n+1 values); v_bounds gets world+1 vertex boundaries: the slot-balanced
+// start (the vertex block that contains the r/world point of the slots; the build finds it on the device with
+// k_shard_bounds) followed by the same cost-model descent desc_b200_build_incidence runs on a multi-GPU handle.
+extern "C" int desc_b200_plan_shards(int32_t n, int32_t world, const int64_t* cum_slots, const int32_t* cum_adj,
+                                     int32_t slots_only, int32_t* v_bounds) {
+    if (n <= 0 || world < 1 || world > 64 || !cum_slots || !cum_adj || !v_bounds) {
+        desc_set_error("plan_shards: bad arguments");
+        return DESC_B200_ERR_ARG;
+    }
+    std::vector<int64_t> cs(cum_slots, cum_slots + n + 1);
+    std::vector<int> ca(cum_adj, cum_adj + n + 1);
+    std::vector<int> vb(world + 1, 0);
+    vb[world] = n;
+    for (int r = 1; r < world; r++) {   // first vertex block starting at or after r/world of the slots (k_shard_bounds + alignment)
+        const int64_t target = (cs[n] * r) / world;
+        int v = (int)(std::lower_bound(cs.begin(), cs.end(), target) - cs.begin());
+        // k_shard_bounds picks the first EDGE whose rowptr >= target and the shard starts at that edge's vertex block
+        if (v > 0 && cs[v] > target) v -= 1;
+        vb[r] = std::min(std::max(v, vb[r - 1]), n);
+    }
+    if (!slots_only && world > 1) cost_model_bounds(cs, ca, n, world, vb);
+    for (int r = 0; r <= world; r++) v_bounds[r] = vb[r];
+    return DESC_B200_OK;
+}
+
 static void free_incidence(desc_b200_handle* h) {
     cudaFree(h->rowptr);
     cudaFree(h->apex);

@@ -277,6 +277,12 @@ int desc_b200_model_fetch(desc_b200_model* mo, double* Ind, double* RijMat, doub
 /* device pointers of the model's buffers (valid until desc_b200_model_destroy) */
 int desc_b200_model_device(desc_b200_model* mo, const double** Ind, const double** RijMat, const double** R_orig,
                            const double** ErrVec);
+/* Host-only (no device needed): the vertex-aligned shard boundaries a multi-GPU handle of `world` ranks would use.
+   cum_slots[v] / cum_adj[v] (n+1 values each) = slots / adjacency entries of the vertex blocks before v; v_bounds gets
+   world+1 boundaries.  slots_only != 0: equal slot counts (round 1); 0: the cost model of csrc/build.cu (pass 1 pays
+   its slots + the tables of its own vertex blocks, pass 2 its slots + the tables of every vertex above its first).  */
+int desc_b200_plan_shards(int32_t n, int32_t world, const int64_t* cum_slots, const int32_t* cum_adj,
+                          int32_t slots_only, int32_t* v_bounds);
 int desc_b200_get_timings(desc_b200_handle* h, desc_b200_timings* t);
 /* synchronise the handle's stream (for callers timing from outside) */
 int desc_b200_sync(desc_b200_handle* h);
