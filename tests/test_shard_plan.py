@@ -69,3 +69,66 @@ def test_degenerate_inputs():
     assert vb[0] == 0 and vb[-1] == 10 and np.all(np.diff(vb) >= 0)
     lib = _lib.load()
     assert lib.desc_b200_plan_shards(C.c_int32(0), C.c_int32(2), None, None, C.c_int32(0), None) == _lib.ERR_ARG
+
+
+def test_sharded_pgd_model_on_cost_model_shards_equals_single_rank():
+    """the N-rank algorithm (oracle/desc_sharded.py, the CPU model of what libdesc_b200 runs on N GPUs) on the UNEQUAL,
+    vertex-aligned shards the cost model produces: same S_vec / history / stop iteration as one rank.  Three ranks as
+    threads of this process; collectives = barriers over shared buffers."""
+    import threading
+    from oracle import desc_oracle as O
+    from oracle.desc_sharded import pgd_sharded
+
+    W = 3
+    mo = O.uniform_topology(90, 0.45, 0.25, 0.05, rng=5)
+    inc = O.build_incidence(mo["Ind"], n_sample=10, seed=2)
+    S0 = O.cycle_inconsistency(inc, mo["RijMat"])
+    n, m = inc.n, inc.m
+    ns_all = np.zeros(m, dtype=np.int64)
+    ns_all[inc.pos_edges] = np.diff(inc.rowptr)
+    rowptr_all = np.concatenate([[0], np.cumsum(ns_all)])
+    estart = np.searchsorted(inc.ei, np.arange(n + 1))                  # first edge of every vertex block
+    deg = np.bincount(inc.ei, minlength=n) + np.bincount(inc.ej, minlength=n)
+    vb = plan(rowptr_all[estart], np.concatenate([[0], np.cumsum(deg)]), W)
+    bounds = estart[vb]                                                 # vertex-aligned edge boundaries
+    assert bounds[0] == 0 and bounds[-1] == m and len(set(np.diff(rowptr_all[bounds]))) > 1   # really unequal
+
+    bar = threading.Barrier(W)
+    box = {"red": [None] * W, "S": None}
+
+    def make(rank):
+        def allreduce(x):
+            box["red"][rank] = np.array(x, dtype=np.float64, copy=True)
+            bar.wait()
+            out = sum(box["red"][r] for r in range(W))                  # same order on every rank
+            bar.wait()
+            return out
+
+        def allgather(S, b):
+            if rank == 0:
+                box["S"] = np.array(S, copy=True)
+            bar.wait()
+            box["S"][b[rank]:b[rank + 1]] = S[b[rank]:b[rank + 1]]
+            bar.wait()
+            out = box["S"].copy()
+            bar.wait()
+            return out
+        return allreduce, allgather
+
+    res = [None] * W
+
+    def run(rank):
+        ar, ag = make(rank)
+        res[rank] = pgd_sharded(inc, S0, 30, 0.02, rank, W, bounds, ar, ag)
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(W)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    S_ref, hist_ref, k_ref = O.pgd(inc, S0, 30, O.ConstantStepSize(0.02))
+    for r in range(W):
+        S, hist, k = res[r]
+        assert k == k_ref
+        assert np.max(np.abs(S - S_ref)) <= 1e-12
+        assert np.max(np.abs(hist[:, 1] - hist_ref[:, 1]) / np.abs(hist_ref[:, 1])) <= 1e-11
